@@ -1,0 +1,10 @@
+"""Import shim: the package lives in ``kokoro-align_b200/`` (a directory name Python cannot
+import directly); this module makes it importable as ``kokoro_align_b200``."""
+import os as _os
+
+_real = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))),
+                      "kokoro-align_b200")
+__path__.insert(0, _real)
+with open(_os.path.join(_real, "__init__.py")) as _f:
+    exec(compile(_f.read(), _os.path.join(_real, "__init__.py"), "exec"))
+del _f
