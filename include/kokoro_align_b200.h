@@ -1,0 +1,121 @@
+/*
+ * kokoro_align_b200.h -- C ABI of the B200-native CTC best-path aligner.
+ *
+ * Drop-in boundary for ONE path of kaiidams/Kokoro-Align: the banded, max_move-transition
+ * CTC best-path alignment
+ *     kokoro_align/align.py:43-109   ctc_best_path(log_probs, labels, beam_size=1000, max_move=4)
+ *     kokoro_align/align.py:21-40    flush_determined_path  (the traceback)
+ * called once per chapter from kokoro_align/align.py:112-124 (best_path) by
+ * run_example.py:247-254.  The reference has no FFI of its own (it is pure Python/numpy);
+ * these entry points are what a ctypes binding in align.py would call -- see INTEGRATION.md.
+ *
+ * Plain pointers and sizes only; no torch / C++ types.  All functions return 0 on success or
+ * a negative KAB_E_* code (kab_error_string() gives text; CUDA errors are reported as
+ * KAB_E_CUDA and the CUDA message is available from kab_last_cuda_error()).
+ * There is no CPU fallback: without a CUDA device every compute entry fails with KAB_E_CUDA.
+ *
+ * Batch layout ("flat batch"):  B independent lattices.
+ *   log_probs  float32 [sum_b T_b, V] row-major, lattice b = rows t_off[b] .. t_off[b+1]
+ *   labels     int32   [sum_b L_b],            lattice b = l_off[b] .. l_off[b+1]
+ *   outputs    best_path int32 [sum T], best_labels int32 [sum T], best_scores float32 [sum T]
+ *              (align.py:105-109), final_score float32 [B] (DP score of the end state,
+ *              internal to the reference), status int32 [B] (KAB_ST_*).
+ * Outputs of a lattice whose status != 0 are unspecified.
+ */
+#ifndef KOKORO_ALIGN_B200_H
+#define KOKORO_ALIGN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KAB_VERSION 100 /* 0.1.0 */
+
+/* return codes */
+#define KAB_OK 0
+#define KAB_E_CUDA (-1)        /* CUDA runtime error, or no device */
+#define KAB_E_BAD_ARG (-2)     /* NULL pointer, negative size, max_move outside 1..16, T_b < 1 */
+#define KAB_E_NOMEM (-3)       /* host allocation failed */
+#define KAB_E_UNSUPPORTED (-4) /* shape outside what the kernels handle (documented per call) */
+
+/* per-lattice status, written to status[b] */
+#define KAB_ST_OK 0
+#define KAB_ST_DEAD_BAND 1 /* no active state in the last frame: reference raises ValueError, align.py:101 */
+#define KAB_ST_BAD_LABEL 2 /* label outside [-V, V): reference raises IndexError, align.py:77 */
+#define KAB_ST_NONFINITE 3 /* a log-prob of the lattice is not finite (rejected) */
+
+/* kernel classes a lattice can be routed to (kab_plan_info) */
+#define KAB_CLASS_WARP 0    /* one warp per lattice, full window, S <= 256, max_move 4 */
+#define KAB_CLASS_BAND 1    /* one CTA per lattice, ring of beam_size+12 states, max_move 4 */
+#define KAB_CLASS_GENERIC 2 /* any beam_size / max_move / label values */
+
+typedef struct kab_plan kab_plan; /* opaque */
+
+typedef struct kab_plan_info {
+  int64_t n_lattices;
+  int64_t n_class[3];       /* lattices per KAB_CLASS_* */
+  int64_t total_frames;     /* sum_b T_b */
+  int64_t cells_eval;       /* sum_b sum_i (hi_i - lo_i): cells the recurrence evaluates */
+  int64_t cells_nominal;    /* sum_b T_b * S_b */
+  int64_t workspace_bytes;  /* device memory held by the plan (backpointers, labels, queues) */
+  int64_t backptr_bytes;    /* of which packed backpointers */
+  int64_t algorithmic_bytes;/* 4*min(V,D+1)*T + cells*b/8 + T*b/8 + 12*T, summed */
+  int32_t kernel_launches;  /* kernels launched by one kab_plan_run_* */
+  int32_t device;
+} kab_plan_info;
+
+int kab_version(void);
+const char *kab_error_string(int code);
+const char *kab_last_cuda_error(void);
+int kab_device_count(int *count);
+
+/*
+ * Build a plan for a fixed batch of transcripts and frame counts (host pointers; copied).
+ * Replaces the label expansion of align.py:46-48 and the per-frame window arithmetic of
+ * align.py:64-65; classifies every lattice, uploads the label tables and allocates the
+ * backpointer workspace on `device`.  beam_size / max_move are align.py:43's keywords.
+ */
+int kab_plan_create(kab_plan **plan, int device, int64_t n_lattices, const int64_t *t_off,
+                    const int32_t *labels, const int64_t *l_off, int32_t vocab_size,
+                    int32_t beam_size, int32_t max_move);
+int kab_plan_get_info(const kab_plan *plan, kab_plan_info *info);
+int kab_plan_destroy(kab_plan *plan);
+
+/*
+ * Run the alignment with every buffer already on the plan's device (align.py:57-107 for all
+ * lattices of the batch).  `stream` is a cudaStream_t (NULL = default stream); the call is
+ * asynchronous with respect to the host.  d_final_score may be NULL.
+ */
+int kab_plan_run_device(kab_plan *plan, const float *d_log_probs, int32_t *d_best_path,
+                        int32_t *d_best_labels, float *d_best_scores, float *d_final_score,
+                        int32_t *d_status, void *stream);
+
+/*
+ * Same, host buffers (pageable or pinned): copies log_probs to the device, runs, copies the
+ * three output arrays, final_score and status back, and returns after everything is complete.
+ */
+int kab_plan_run_host(kab_plan *plan, const float *h_log_probs, int32_t *h_best_path,
+                      int32_t *h_best_labels, float *h_best_scores, float *h_final_score,
+                      int32_t *h_status);
+
+/*
+ * One-shot single lattice with host buffers == kokoro_align/align.py:43
+ * ctc_best_path(log_probs[T,V], labels[L], beam_size, max_move) -> (best_path, best_labels,
+ * best_scores); *status receives KAB_ST_*; final_score may be NULL.
+ */
+int kab_ctc_best_path(const float *log_probs, int64_t T, int32_t vocab_size, const int32_t *labels,
+                      int64_t L, int32_t beam_size, int32_t max_move, int32_t *best_path,
+                      int32_t *best_labels, float *best_scores, float *final_score,
+                      int32_t *status);
+
+/* Pinned host memory for kab_plan_run_host callers (cudaHostAlloc / cudaFreeHost). */
+int kab_host_alloc(void **ptr, size_t bytes);
+int kab_host_free(void *ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KOKORO_ALIGN_B200_H */

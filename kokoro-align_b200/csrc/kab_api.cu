@@ -1,0 +1,390 @@
+// kab_api.cu -- C ABI (include/kokoro_align_b200.h) over the sm_100a CTC best-path kernels.
+//
+// Host side of the drop-in boundary for kokoro_align/align.py:43-109: lattice
+// classification, label tables (align.py:46-48), backpointer workspace, launches.
+// No CPU fallback: every compute entry needs a CUDA device.
+#include "../../include/kokoro_align_b200.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "kab_band.cuh"
+#include "kab_common.cuh"
+#include "kab_generic.cuh"
+#include "kab_warp.cuh"
+
+namespace {
+
+thread_local char g_cuda_err[512] = "";
+
+int cuda_fail(cudaError_t e, const char *what) {
+  snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", what, cudaGetErrorString(e));
+  return KAB_E_CUDA;
+}
+#define KAB_CUDA(call)                                    \
+  do {                                                    \
+    cudaError_t e_ = (call);                              \
+    if (e_ != cudaSuccess) return cuda_fail(e_, #call);   \
+  } while (0)
+
+// kernel classes: 0 warp, 1..4 band with NT = 128/256/512/1024, 5 generic
+constexpr int N_QUEUES = 6;
+constexpr int Q_WARP = 0, Q_BAND0 = 1, Q_GENERIC = 5;
+constexpr int kBandNT[4] = {128, 256, 512, 1024};
+constexpr int GENERIC_NT = 256;
+constexpr int MAX_STAGE_V = 128;  // widest vocabulary the staged (warp / band) kernels take
+
+inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+int64_t cells_eval_of(int64_t T, int64_t S, int64_t W) {
+  // sum_i (hi_i - lo_i), align.py:64-65.  Closed form when the window never clips.
+  if (W >= S && (S * (T - 1)) / T <= W / 2) return T * S;
+  int64_t cells = 0;
+  for (int64_t i = 0; i < T; ++i) {
+    int64_t lo = std::max<int64_t>(0, (S * i) / T - W / 2);
+    int64_t hi = std::min(lo + W, S);
+    if (hi > lo) cells += hi - lo;
+  }
+  return cells;
+}
+
+}  // namespace
+
+struct kab_plan {
+  int device = 0;
+  int64_t B = 0, total_T = 0, total_L = 0;
+  int32_t V = 0, W = 0, M = 0;
+  int sm_count = 0;
+  int32_t stage_frames = 0, stage_bytes = 0;
+  kab_plan_info info{};
+  std::vector<KabLattice> lists[N_QUEUES];
+  bool any_bad_label = false;
+  // device memory
+  KabLattice *d_lists[N_QUEUES] = {};
+  uint16_t *d_col16 = nullptr;
+  int32_t *d_raw = nullptr;
+  uint8_t *d_bp = nullptr;
+  float *d_scratch = nullptr;
+  unsigned int *d_queue = nullptr;
+  int32_t *d_status_init = nullptr;
+  // launch geometry
+  int grid[N_QUEUES] = {};
+  size_t smem[N_QUEUES] = {};
+  // buffers of kab_plan_run_host
+  cudaStream_t stream = nullptr;
+  float *d_lp = nullptr;
+  int32_t *d_path = nullptr, *d_lab = nullptr, *d_st = nullptr;
+  float *d_sc = nullptr, *d_fs = nullptr;
+};
+
+namespace {
+
+template <int NT>
+int band_setup(kab_plan *pl, int q) {
+  const size_t smem = kab_band_smem_fixed<NT>() + (size_t)KAB_BAND_STAGES * pl->stage_bytes;
+  KAB_CUDA(cudaFuncSetAttribute(kab_band_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  KAB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kab_band_kernel<NT>, NT, smem));
+  pl->smem[q] = smem;
+  pl->grid[q] = (int)std::min<int64_t>((int64_t)pl->lists[q].size(), (int64_t)pl->sm_count * std::max(occ, 1));
+  return KAB_OK;
+}
+
+int plan_free(kab_plan *pl) {
+  if (!pl) return KAB_OK;
+  cudaSetDevice(pl->device);
+  for (int q = 0; q < N_QUEUES; ++q) cudaFree(pl->d_lists[q]);
+  cudaFree(pl->d_col16); cudaFree(pl->d_raw); cudaFree(pl->d_bp); cudaFree(pl->d_scratch);
+  cudaFree(pl->d_queue); cudaFree(pl->d_status_init);
+  cudaFree(pl->d_lp); cudaFree(pl->d_path); cudaFree(pl->d_lab); cudaFree(pl->d_st);
+  cudaFree(pl->d_sc); cudaFree(pl->d_fs);
+  if (pl->stream) cudaStreamDestroy(pl->stream);
+  delete pl;
+  return KAB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int kab_version(void) { return KAB_VERSION; }
+
+const char *kab_error_string(int code) {
+  switch (code) {
+    case KAB_OK: return "ok";
+    case KAB_E_CUDA: return "CUDA error (see kab_last_cuda_error)";
+    case KAB_E_BAD_ARG: return "bad argument";
+    case KAB_E_NOMEM: return "out of host memory";
+    case KAB_E_UNSUPPORTED: return "unsupported shape";
+    default: return "unknown error";
+  }
+}
+
+const char *kab_last_cuda_error(void) { return g_cuda_err; }
+
+int kab_device_count(int *count) {
+  if (!count) return KAB_E_BAD_ARG;
+  KAB_CUDA(cudaGetDeviceCount(count));
+  return KAB_OK;
+}
+
+int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off, const int32_t *labels,
+                    const int64_t *l_off, int32_t V, int32_t W, int32_t M) {
+  if (!out || B < 0 || !t_off || !l_off || V < 1 || V > 65535 || W < 0 || M < 1 || M > 255) return KAB_E_BAD_ARG;
+  if (B > 0 && (t_off[0] < 0 || l_off[0] < 0)) return KAB_E_BAD_ARG;
+  if (B > 0 && l_off[B] > l_off[0] && !labels) return KAB_E_BAD_ARG;
+  for (int64_t b = 0; b < B; ++b) {
+    const int64_t T = t_off[b + 1] - t_off[b], L = l_off[b + 1] - l_off[b];
+    if (T < 1 || T > 0x3fffffff || L < 0 || L > 0x3ffffff0) return KAB_E_BAD_ARG;
+  }
+  KAB_CUDA(cudaSetDevice(device));
+  kab_plan *pl = new (std::nothrow) kab_plan();
+  if (!pl) return KAB_E_NOMEM;
+  pl->device = device; pl->B = B; pl->V = V; pl->W = W; pl->M = M;
+  pl->total_T = B ? t_off[B] : 0;  // offsets are absolute rows / entries of the caller's arrays
+  pl->total_L = B ? l_off[B] : 0;
+  cudaDeviceProp prop;
+  cudaError_t ce = cudaGetDeviceProperties(&prop, device);
+  if (ce != cudaSuccess) { delete pl; return cuda_fail(ce, "cudaGetDeviceProperties"); }
+  pl->sm_count = prop.multiProcessorCount;
+
+  // emission staging geometry: ~4 KB stages, at most 16 frames each
+  pl->stage_frames = std::max(1, std::min(16, 4096 / (V * 4)));
+  pl->stage_bytes = (int32_t)align_up((int64_t)pl->stage_frames * V * 4 + 24, 16);
+
+  // ---- classify, build the padded column table (numpy-style wrap of negative labels)
+  std::vector<uint16_t> col16;
+  std::vector<int32_t> status_init((size_t)B, 0);
+  col16.reserve((size_t)(pl->total_L + 16 * B + 16));
+  int64_t bp_bytes = 0, scr_floats = 0;
+  kab_plan_info &info = pl->info;
+  info.n_lattices = B; info.device = device; info.total_frames = pl->total_T;
+  for (int64_t b = 0; b < B; ++b) {
+    const int64_t T = t_off[b + 1] - t_off[b], L = l_off[b + 1] - l_off[b], S = 2 * L + 1;
+    const int32_t *lab = labels + l_off[b];
+    bool bad = false, special = false;
+    int64_t distinct_mask[1024] = {0};
+    int64_t distinct = 0;
+    for (int64_t l = 0; l < L; ++l) {
+      if (lab[l] < -V || lab[l] >= V) { bad = true; break; }
+      if (lab[l] <= 0) special = true;
+      const int32_t c = lab[l] < 0 ? lab[l] + V : lab[l];
+      if (!(distinct_mask[c >> 6] >> (c & 63) & 1)) { distinct_mask[c >> 6] |= (int64_t)1 << (c & 63); ++distinct; }
+    }
+    if (bad) {  // reference: IndexError at align.py:77
+      status_init[(size_t)b] = KAB_ST_BAD_LABEL;
+      pl->any_bad_label = true;
+      continue;
+    }
+    KabLattice d{};
+    d.t_off = t_off[b];
+    d.lab_off = l_off[b];
+    d.T = (int32_t)T; d.L = (int32_t)L; d.index = (int32_t)b;
+    d.col_off = (int64_t)col16.size();
+    for (int64_t l = 0; l < L; ++l) col16.push_back((uint16_t)(lab[l] < 0 ? lab[l] + V : lab[l]));
+    while (col16.size() % 8) col16.push_back(0);
+    for (int k = 0; k < 8; ++k) col16.push_back(0);
+
+    const bool fast = M == 4 && !special && V <= MAX_STAGE_V;
+    const bool full = W >= S && (S * (T - 1)) / T <= W / 2;
+    const int64_t weff = std::min<int64_t>(W, S);
+    int q;
+    if (fast && full && S <= 256) {
+      q = Q_WARP;
+      d.k = S <= 64 ? 2 : (S <= 128 ? 4 : (S <= 192 ? 6 : 8));
+      const int fpw = d.k <= 2 ? 8 : (d.k <= 4 ? 4 : 2);
+      d.bp_off = bp_bytes;
+      bp_bytes += align_up((T + fpw - 1) / fpw * 128, 256);
+    } else if (fast && W >= 1 && S <= 3 * T && weff + 12 <= 4096) {
+      int nt_idx = weff + 12 <= 512 ? 0 : (weff + 12 <= 1024 ? 1 : (weff + 12 <= 2048 ? 2 : 3));
+      q = Q_BAND0 + nt_idx;
+      d.bp_off = bp_bytes;
+      bp_bytes += align_up((T + 3) / 4 * kBandNT[nt_idx] * 4, 256);
+    } else {
+      q = Q_GENERIC;
+      d.bp_off = bp_bytes;
+      bp_bytes += align_up(T * std::max<int64_t>(1, weff), 256);
+      d.scr_off = scr_floats;
+      scr_floats += align_up(2 * (S + 16), 64);
+    }
+    pl->lists[q].push_back(d);
+    info.n_class[q == Q_WARP ? KAB_CLASS_WARP : (q == Q_GENERIC ? KAB_CLASS_GENERIC : KAB_CLASS_BAND)]++;
+    const int64_t cells = cells_eval_of(T, S, W);
+    info.cells_eval += cells;
+    info.cells_nominal += T * S;
+    int bbits = 0;
+    while ((1 << bbits) < M) ++bbits;
+    const int64_t dcols = std::min<int64_t>(V, distinct + 1);
+    info.algorithmic_bytes += 4 * dcols * T + (cells * bbits + 7) / 8 + (T * bbits + 7) / 8 + 12 * T;
+  }
+  // longest-processing-time-first order inside every queue
+  for (int q = 0; q < N_QUEUES; ++q)
+    std::stable_sort(pl->lists[q].begin(), pl->lists[q].end(), [&](const KabLattice &a, const KabLattice &b2) {
+      const int64_t ca = (int64_t)a.T * (q == Q_WARP ? a.k : 1), cb = (int64_t)b2.T * (q == Q_WARP ? b2.k : 1);
+      return ca > cb;
+    });
+
+  // ---- device allocations
+  int rc = KAB_OK;
+  auto up = [&](void **dst, const void *src, size_t bytes) -> int {
+    if (!bytes) return KAB_OK;
+    KAB_CUDA(cudaMalloc(dst, bytes));
+    KAB_CUDA(cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
+    return KAB_OK;
+  };
+  do {
+    for (int q = 0; q < N_QUEUES && rc == KAB_OK; ++q)
+      rc = up((void **)&pl->d_lists[q], pl->lists[q].data(), pl->lists[q].size() * sizeof(KabLattice));
+    if (rc) break;
+    if ((rc = up((void **)&pl->d_col16, col16.data(), col16.size() * sizeof(uint16_t)))) break;
+    if (!pl->lists[Q_GENERIC].empty())
+      if ((rc = up((void **)&pl->d_raw, labels, (size_t)pl->total_L * sizeof(int32_t)))) break;
+    if (pl->any_bad_label)
+      if ((rc = up((void **)&pl->d_status_init, status_init.data(), (size_t)B * sizeof(int32_t)))) break;
+    cudaError_t e;
+    if (bp_bytes && (e = cudaMalloc((void **)&pl->d_bp, (size_t)bp_bytes)) != cudaSuccess) { rc = cuda_fail(e, "cudaMalloc(backpointers)"); break; }
+    if (scr_floats && (e = cudaMalloc((void **)&pl->d_scratch, (size_t)scr_floats * 4)) != cudaSuccess) { rc = cuda_fail(e, "cudaMalloc(scratch)"); break; }
+    if ((e = cudaMalloc((void **)&pl->d_queue, N_QUEUES * sizeof(unsigned int))) != cudaSuccess) { rc = cuda_fail(e, "cudaMalloc(queue)"); break; }
+
+    // ---- launch geometry
+    if (!pl->lists[Q_WARP].empty()) {
+      const size_t smem = 128 + (size_t)KAB_WARPS_PER_CTA * KAB_WARP_STAGES * pl->stage_bytes;
+      if ((e = cudaFuncSetAttribute(kab_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) { rc = cuda_fail(e, "cudaFuncSetAttribute(warp)"); break; }
+      int occ = 0;
+      if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kab_warp_kernel, KAB_WARPS_PER_CTA * 32, smem)) != cudaSuccess) { rc = cuda_fail(e, "occupancy(warp)"); break; }
+      pl->smem[Q_WARP] = smem;
+      const int64_t ctas = ((int64_t)pl->lists[Q_WARP].size() + KAB_WARPS_PER_CTA - 1) / KAB_WARPS_PER_CTA;
+      pl->grid[Q_WARP] = (int)std::min<int64_t>(ctas, (int64_t)pl->sm_count * std::max(occ, 1));
+    }
+    if (!pl->lists[Q_BAND0 + 0].empty() && (rc = band_setup<128>(pl, Q_BAND0 + 0))) break;
+    if (!pl->lists[Q_BAND0 + 1].empty() && (rc = band_setup<256>(pl, Q_BAND0 + 1))) break;
+    if (!pl->lists[Q_BAND0 + 2].empty() && (rc = band_setup<512>(pl, Q_BAND0 + 2))) break;
+    if (!pl->lists[Q_BAND0 + 3].empty() && (rc = band_setup<1024>(pl, Q_BAND0 + 3))) break;
+    if (!pl->lists[Q_GENERIC].empty())
+      pl->grid[Q_GENERIC] = (int)std::min<int64_t>((int64_t)pl->lists[Q_GENERIC].size(), (int64_t)pl->sm_count * 4);
+  } while (0);
+  if (rc != KAB_OK) { plan_free(pl); return rc; }
+
+  info.backptr_bytes = bp_bytes;
+  info.workspace_bytes = bp_bytes + scr_floats * 4 + (int64_t)col16.size() * 2 +
+                         (pl->d_raw ? pl->total_L * 4 : 0) + B * (int64_t)sizeof(KabLattice);
+  info.kernel_launches = 0;
+  for (int q = 0; q < N_QUEUES; ++q) info.kernel_launches += pl->lists[q].empty() ? 0 : 1;
+  *out = pl;
+  return KAB_OK;
+}
+
+int kab_plan_get_info(const kab_plan *pl, kab_plan_info *info) {
+  if (!pl || !info) return KAB_E_BAD_ARG;
+  *info = pl->info;
+  return KAB_OK;
+}
+
+int kab_plan_destroy(kab_plan *pl) { return plan_free(pl); }
+
+int kab_plan_run_device(kab_plan *pl, const float *d_log_probs, int32_t *d_best_path, int32_t *d_best_labels,
+                        float *d_best_scores, float *d_final_score, int32_t *d_status, void *stream_) {
+  if (!pl) return KAB_E_BAD_ARG;
+  if (pl->B == 0) return KAB_OK;
+  if (!d_log_probs || !d_best_path || !d_best_labels || !d_best_scores || !d_status) return KAB_E_BAD_ARG;
+  if (reinterpret_cast<uintptr_t>(d_log_probs) & 15) return KAB_E_BAD_ARG;  // bulk copies need 16-byte alignment
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  KAB_CUDA(cudaSetDevice(pl->device));
+  KabParams p{};
+  p.lp = d_log_probs;
+  p.lp_bytes = pl->total_T * (int64_t)pl->V * 4;
+  p.col16 = pl->d_col16; p.raw = pl->d_raw; p.bp = pl->d_bp; p.scratch = pl->d_scratch;
+  p.best_path = d_best_path; p.best_labels = d_best_labels; p.best_scores = d_best_scores;
+  p.final_score = d_final_score; p.status = d_status;
+  p.V = pl->V; p.W = pl->W; p.M = pl->M;
+  p.stage_frames = pl->stage_frames; p.stage_bytes = pl->stage_bytes;
+
+  KAB_CUDA(cudaMemsetAsync(pl->d_queue, 0, N_QUEUES * sizeof(unsigned int), stream));
+  if (pl->any_bad_label)
+    KAB_CUDA(cudaMemcpyAsync(d_status, pl->d_status_init, (size_t)pl->B * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
+
+  if (!pl->lists[Q_WARP].empty()) {
+    KabParams pw = p; pw.queue = pl->d_queue + Q_WARP;
+    kab_warp_kernel<<<pl->grid[Q_WARP], KAB_WARPS_PER_CTA * 32, pl->smem[Q_WARP], stream>>>(
+        pl->d_lists[Q_WARP], (int)pl->lists[Q_WARP].size(), pw);
+  }
+  for (int b = 0; b < 4; ++b) {
+    const int q = Q_BAND0 + b;
+    if (pl->lists[q].empty()) continue;
+    KabParams pb = p; pb.queue = pl->d_queue + q;
+    const int n = (int)pl->lists[q].size();
+    switch (b) {
+      case 0: kab_band_kernel<128><<<pl->grid[q], 128, pl->smem[q], stream>>>(pl->d_lists[q], n, pb); break;
+      case 1: kab_band_kernel<256><<<pl->grid[q], 256, pl->smem[q], stream>>>(pl->d_lists[q], n, pb); break;
+      case 2: kab_band_kernel<512><<<pl->grid[q], 512, pl->smem[q], stream>>>(pl->d_lists[q], n, pb); break;
+      default: kab_band_kernel<1024><<<pl->grid[q], 1024, pl->smem[q], stream>>>(pl->d_lists[q], n, pb); break;
+    }
+  }
+  if (!pl->lists[Q_GENERIC].empty()) {
+    KabParams pg = p; pg.queue = pl->d_queue + Q_GENERIC;
+    kab_generic_kernel<GENERIC_NT><<<pl->grid[Q_GENERIC], GENERIC_NT, 0, stream>>>(
+        pl->d_lists[Q_GENERIC], (int)pl->lists[Q_GENERIC].size(), pg);
+  }
+  KAB_CUDA(cudaGetLastError());
+  return KAB_OK;
+}
+
+int kab_plan_run_host(kab_plan *pl, const float *h_log_probs, int32_t *h_best_path, int32_t *h_best_labels,
+                      float *h_best_scores, float *h_final_score, int32_t *h_status) {
+  if (!pl) return KAB_E_BAD_ARG;
+  if (pl->B == 0) return KAB_OK;
+  if (!h_log_probs || !h_best_path || !h_best_labels || !h_best_scores || !h_status) return KAB_E_BAD_ARG;
+  KAB_CUDA(cudaSetDevice(pl->device));
+  const size_t n = (size_t)pl->total_T, B = (size_t)pl->B;
+  if (!pl->stream) {
+    KAB_CUDA(cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking));
+    KAB_CUDA(cudaMalloc((void **)&pl->d_lp, n * pl->V * 4));
+    KAB_CUDA(cudaMalloc((void **)&pl->d_path, n * 4));
+    KAB_CUDA(cudaMalloc((void **)&pl->d_lab, n * 4));
+    KAB_CUDA(cudaMalloc((void **)&pl->d_sc, n * 4));
+    KAB_CUDA(cudaMalloc((void **)&pl->d_fs, B * 4));
+    KAB_CUDA(cudaMalloc((void **)&pl->d_st, B * 4));
+  }
+  cudaStream_t s = pl->stream;
+  KAB_CUDA(cudaMemcpyAsync(pl->d_lp, h_log_probs, n * pl->V * 4, cudaMemcpyHostToDevice, s));
+  int rc = kab_plan_run_device(pl, pl->d_lp, pl->d_path, pl->d_lab, pl->d_sc, pl->d_fs, pl->d_st, s);
+  if (rc != KAB_OK) return rc;
+  KAB_CUDA(cudaMemcpyAsync(h_best_path, pl->d_path, n * 4, cudaMemcpyDeviceToHost, s));
+  KAB_CUDA(cudaMemcpyAsync(h_best_labels, pl->d_lab, n * 4, cudaMemcpyDeviceToHost, s));
+  KAB_CUDA(cudaMemcpyAsync(h_best_scores, pl->d_sc, n * 4, cudaMemcpyDeviceToHost, s));
+  if (h_final_score) KAB_CUDA(cudaMemcpyAsync(h_final_score, pl->d_fs, B * 4, cudaMemcpyDeviceToHost, s));
+  KAB_CUDA(cudaMemcpyAsync(h_status, pl->d_st, B * 4, cudaMemcpyDeviceToHost, s));
+  KAB_CUDA(cudaStreamSynchronize(s));
+  return KAB_OK;
+}
+
+int kab_ctc_best_path(const float *log_probs, int64_t T, int32_t V, const int32_t *labels, int64_t L,
+                      int32_t beam_size, int32_t max_move, int32_t *best_path, int32_t *best_labels,
+                      float *best_scores, float *final_score, int32_t *status) {
+  if (!status) return KAB_E_BAD_ARG;
+  const int64_t t_off[2] = {0, T}, l_off[2] = {0, L};
+  int dev = 0;
+  KAB_CUDA(cudaGetDevice(&dev));
+  kab_plan *pl = nullptr;
+  int rc = kab_plan_create(&pl, dev, 1, t_off, labels, l_off, V, beam_size, max_move);
+  if (rc != KAB_OK) return rc;
+  rc = kab_plan_run_host(pl, log_probs, best_path, best_labels, best_scores, final_score, status);
+  kab_plan_destroy(pl);
+  return rc;
+}
+
+int kab_host_alloc(void **ptr, size_t bytes) {
+  if (!ptr) return KAB_E_BAD_ARG;
+  KAB_CUDA(cudaHostAlloc(ptr, bytes, cudaHostAllocDefault));
+  return KAB_OK;
+}
+
+int kab_host_free(void *ptr) {
+  KAB_CUDA(cudaFreeHost(ptr));
+  return KAB_OK;
+}
+
+}  // extern "C"

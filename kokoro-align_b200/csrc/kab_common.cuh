@@ -1,0 +1,138 @@
+// kab_common.cuh -- shared device helpers for the CTC best-path kernels (sm_100a).
+//
+// The recurrence implemented by every kernel is the reference's
+// kokoro_align/align.py:43-109 (see SURVEY.md section 8a for the per-cell restatement):
+//   cand_j = fl32(score_{i-1}[v-j] + lp[i, ext[v]]),  j = 0..M-1, strict '>' scan in j order,
+//   even j > 0 forbidden into states with ext[v] == 0, window [lo_i, hi_i) per frame,
+//   virtual start state 0 with score 0, forced end at the highest active state.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define KAB_FULL_MASK 0xffffffffu
+
+// Per-lattice work descriptor (device array, one list per kernel class, sorted by cost).
+struct KabLattice {
+  int64_t t_off;    // first row of this lattice in log_probs / the output arrays
+  int64_t col_off;  // first entry in the padded uint16 column table (fast kernels)
+  int64_t lab_off;  // first entry in the raw int32 label table (generic kernel)
+  int64_t bp_off;   // byte offset of this lattice's backpointers in the workspace
+  int64_t scr_off;  // float offset of the generic kernel's two score rows
+  int32_t T;        // frames
+  int32_t L;        // labels; S = 2L+1 extended states
+  int32_t index;    // position in the caller's batch (final_score / status slot)
+  int32_t k;        // class parameter: states per lane (warp kernel)
+};
+
+struct KabParams {
+  const float *lp;          // [sum T, V]
+  int64_t lp_bytes;         // total bytes of lp (bulk copies never read past it)
+  const uint16_t *col16;    // numpy-style column index of every label, padded per lattice
+  const int32_t *raw;       // raw label values (generic kernel: value-based blank test)
+  uint8_t *bp;              // backpointer workspace
+  float *scratch;           // generic kernel score rows
+  int32_t *best_path;       // [sum T]
+  int32_t *best_labels;     // [sum T]
+  float *best_scores;       // [sum T]
+  float *final_score;       // [B] or nullptr
+  int32_t *status;          // [B]
+  unsigned int *queue;      // this kernel class's work-queue counter
+  int32_t V, W, M;
+  int32_t stage_frames;     // emission frames per bulk-copy stage
+  int32_t stage_bytes;      // bytes of one stage buffer (multiple of 16)
+};
+
+__device__ __forceinline__ float kab_neg_inf() { return __int_as_float(0xff800000); }
+__device__ __forceinline__ bool kab_finite(float x) { return fabsf(x) < __int_as_float(0x7f800000); }
+
+// ---------------------------------------------------------------- mbarrier + 1-D bulk copy (TMA)
+__device__ __forceinline__ uint32_t kab_smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void kab_mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(kab_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void kab_fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void kab_mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(kab_smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool kab_mbar_try_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(kab_smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void kab_mbar_wait(uint64_t *bar, uint32_t parity) {
+  while (!kab_mbar_try_wait(bar, parity)) {
+  }
+}
+// global -> shared bulk copy; completion is signalled on `bar` (complete_tx::bytes).
+__device__ __forceinline__ void kab_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   kab_smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(kab_smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void kab_fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// ---------------------------------------------------------------- emission staging
+// Frames [f0, f0+nf) of a lattice are rows of V floats starting at byte b0 of lp.  Rows are only
+// 4-byte aligned (V = 39 -> 156 B), bulk copies need 16-byte alignment, so a stage fetches the
+// enclosing 16-byte aligned span and readers add `skew` words.  A span end that would run
+// past the end of lp is clamped and the (< 16 B) remainder is fetched with plain loads.
+struct KabStageDesc {
+  const char *src;     // 16-byte aligned global address
+  uint32_t bytes;      // multiple of 16 (may be 0)
+  uint32_t skew;       // word index of frame f0 column 0 inside the stage buffer
+  uint32_t tail_word;  // first word index not covered by the bulk copy
+  uint32_t tail_n;     // number of trailing words to copy with plain loads (0..3)
+};
+
+__device__ __forceinline__ KabStageDesc kab_stage_desc(const KabParams &p, int64_t t_off, int32_t f0,
+                                                       int32_t nf) {
+  KabStageDesc d;
+  const int64_t b0 = (t_off + f0) * (int64_t)p.V * 4;
+  const int64_t b1 = b0 + (int64_t)nf * p.V * 4;
+  const int64_t a0 = b0 & ~(int64_t)15;
+  int64_t a1 = (b1 + 15) & ~(int64_t)15;
+  if (a1 > p.lp_bytes) a1 = b1 & ~(int64_t)15;
+  if (a1 < a0) a1 = a0;
+  d.src = reinterpret_cast<const char *>(p.lp) + a0;
+  d.bytes = (uint32_t)(a1 - a0);
+  d.skew = (uint32_t)((b0 - a0) >> 2);
+  d.tail_word = d.bytes >> 2;
+  d.tail_n = a1 < b1 ? (uint32_t)((b1 - a1) >> 2) : 0u;
+  return d;
+}
+
+// ---------------------------------------------------------------- the two cell updates (M = 4)
+// Blank state (ext[v] == 0): moves 0, 1, 3 (move 2 = blank -> blank is forbidden, align.py:80-81).
+// Every candidate is one IEEE fp32 add (align.py:77); the scan is strict '>' in j order
+// (np.argmax returns the first maximum, align.py:83), so the smallest move wins ties.
+__device__ __forceinline__ float kab_cell_blank(float s0, float s1, float s3, float e, uint32_t &mv) {
+  const float a0 = __fadd_rn(s0, e), a1 = __fadd_rn(s1, e), a3 = __fadd_rn(s3, e);
+  const bool p1 = a1 > a0;
+  const float m = p1 ? a1 : a0;
+  const bool p3 = a3 > m;
+  mv = p3 ? 3u : (p1 ? 1u : 0u);
+  return p3 ? a3 : m;
+}
+// Label state: moves 0, 1, 2, 3.  Tournament form of the same ascending strict-'>' scan:
+// the winner of (0,1) vs the winner of (2,3); the upper pair wins only if strictly greater.
+__device__ __forceinline__ float kab_cell_label(float s0, float s1, float s2, float s3, float e,
+                                                uint32_t &mv) {
+  const float a0 = __fadd_rn(s0, e), a1 = __fadd_rn(s1, e), a2 = __fadd_rn(s2, e), a3 = __fadd_rn(s3, e);
+  const bool p01 = a1 > a0, p23 = a3 > a2;
+  const float m01 = p01 ? a1 : a0, m23 = p23 ? a3 : a2;
+  const bool ph = m23 > m01;
+  mv = ph ? (p23 ? 3u : 2u) : (p01 ? 1u : 0u);
+  return ph ? m23 : m01;
+}

@@ -1,0 +1,19 @@
+"""Phoneme vocabulary of the acoustic model (the data contract of encoder.py:5-19 in the
+reference): 39 symbols, index 0 ('_') is the CTC blank; tokens outside the table are dropped
+when a transcript is encoded; ids are int8."""
+import numpy as np
+
+VOCAB = ('_', 'N', 'a', 'a:', 'b', 'by', 'ch', 'd', 'e', 'e:', 'f', 'g', 'gy', 'h', 'hy', 'i',
+         'i:', 'j', 'k', 'ky', 'm', 'my', 'n', 'ny', 'o', 'o:', 'p', 'py', 'r', 'ry', 's', 'sh',
+         't', 'ts', 'u', 'u:', 'w', 'y', 'z')
+VOCAB_SIZE = len(VOCAB)
+_INDEX = {tok: n for n, tok in enumerate(VOCAB)}
+
+
+def encode_text(text):
+    ids = [_INDEX[tok] for tok in text.split() if tok in _INDEX]
+    return np.array(ids, dtype=np.int8)
+
+
+def decode_text(encoded):
+    return ' '.join(VOCAB[n] for n in encoded)

@@ -1,0 +1,78 @@
+"""CPU-side checks of the boundary: the C-ABI library builds/loads and exports every symbol
+include/kokoro_align_b200.h declares; the host mirror keeps the reference's signatures; the
+product path fails loudly without a CUDA device (no CPU fallback)."""
+import ctypes
+import inspect
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "kokoro_align_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(kab_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from kokoro_align_b200 import _lib
+    L = _lib.lib()
+    names = _declared_symbols()
+    assert len(names) >= 12
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in the header but not exported"
+    assert sorted(_lib.EXPORTS) == names
+    assert L.kab_version() == 100
+    assert L.kab_error_string(-2) == b"bad argument"
+
+
+def test_reference_signatures():
+    from kokoro_align_b200 import align
+    sig = inspect.signature(align.ctc_best_path)
+    assert list(sig.parameters)[:4] == ["log_probs", "labels", "beam_size", "max_move"]
+    assert sig.parameters["beam_size"].default == 1000 and sig.parameters["max_move"].default == 4
+    assert list(inspect.signature(align.best_path).parameters) == ["input_file", "voca_file", "output_file"]
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from kokoro_align_b200 import align
+    with pytest.raises(align.KabError):
+        align.ctc_best_path(np.zeros((4, 5), np.float32), np.array([1], np.int8))
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "kokoro-align_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("no oracle", ""), f"{f} mentions the oracle"
+
+
+def test_argument_errors_match_reference():
+    from kokoro_align_b200 import align
+    with pytest.raises(IndexError):
+        align.ctc_best_path(np.zeros((0, 5), np.float32), np.array([1], np.int8))
+    with pytest.raises(ValueError):
+        align.ctc_best_path(np.zeros((3, 5), np.float32), np.array([1], np.int8), max_move=0)
+
+
+def test_encoder_contract():
+    from kokoro_align_b200 import encoder
+    assert encoder.VOCAB_SIZE == 39 and encoder.VOCAB[0] == "_"
+    ids = encoder.encode_text("a k a q . N zz")
+    assert ids.dtype == np.int8 and ids.tolist() == [2, 18, 2, 1]
+
+
+def test_transcript_labels(tmp_path):
+    from kokoro_align_b200 import align
+    p = tmp_path / "x.voca.txt"
+    p.write_text("こん|k o N\nにちは|n i ch i w a .\n")
+    assert align.read_transcript_labels(str(p)).tolist() == [18, 24, 1, 22, 15, 6, 15, 36, 2]

@@ -1,0 +1,141 @@
+"""Parity of the CUDA path (through the C ABI) with the reference's golden vectors and with
+the CPU oracle on seeded inputs.  Bit-exact for best_path / best_labels / best_scores;
+final score within 1e-4 relative (north_star) -- asserted bit-equal in practice."""
+import numpy as np
+import pytest
+
+from tests.golden_util import check_case, golden_names
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def kab():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from kokoro_align_b200 import align
+    return align
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_golden(golden, kab, name):
+    index, arrays = golden
+    case = next(c for c in index if c["name"] == name)
+    check_case(case, arrays, kab.ctc_best_path)
+
+
+def _compare_batch(kab, lp, t_off, labels, l_off, beam_size=1000, max_move=4, V=39, threads=8):
+    from oracle import ctc_oracle
+    rp, rl, rs, rf, rst = ctc_oracle.ctc_best_path_batch(lp, t_off, labels, l_off, beam_size,
+                                                         max_move, n_threads=threads)
+    with kab.AlignPlan(t_off, labels, l_off, V, beam_size, max_move) as plan:
+        path, labs, scores, final, status = plan.run_host(lp)
+        info = plan.info
+    np.testing.assert_array_equal(status, rst)
+    for b in range(len(t_off) - 1):
+        if rst[b] != 0:
+            continue
+        a, e = int(t_off[b]), int(t_off[b + 1])
+        np.testing.assert_array_equal(path[a:e], rp[a:e], err_msg=f"lattice {b}")
+        np.testing.assert_array_equal(labs[a:e], rl[a:e], err_msg=f"lattice {b}")
+        assert scores[a:e].tobytes() == rs[a:e].tobytes(), f"lattice {b}"
+        assert abs(float(final[b]) - float(rf[b])) <= 1e-4 * max(1.0, abs(float(rf[b])))
+        assert final[b].tobytes() == rf[b].tobytes(), f"lattice {b}"
+    return info
+
+
+def test_batch_short_segments(kab):
+    """Config-2-shaped batch (warp kernel, all K classes), iid Gaussian log-softmax."""
+    from kokoro_align_b200 import synth
+    T, L = synth.segment_lengths(300, seed=2000)
+    lp, t_off, labels, l_off = synth.make_batch_fast(T, L, seed=2001)
+    info = _compare_batch(kab, lp, t_off, labels, l_off)
+    assert info.n_class[0] == 300 and info.cells_eval == int((T * (2 * L + 1)).sum())
+
+
+def test_batch_short_segments_ties(kab):
+    from kokoro_align_b200 import synth
+    T, L = synth.segment_lengths(200, seed=2100, t_min=1, t_max=400)
+    lp, t_off, labels, l_off = synth.make_batch(T, L, seed=2101)
+    lp = (np.round(lp * 2) / 2).astype(np.float32)
+    _compare_batch(kab, lp, t_off, labels, l_off)
+
+
+def test_batch_mixed_classes(kab):
+    """One batch that exercises warp, band (two ring sizes) and generic kernels at once,
+    including a bad-label lattice and a dead band."""
+    from kokoro_align_b200 import synth
+    T = np.array([300, 2500, 50, 4000, 700, 90, 1200, 10, 640])
+    L = np.array([40, 900, 5, 1500, 300, 100, 170, 40, 90])
+    lp, t_off, labels, l_off = synth.make_batch(T, L, seed=3000, planted=True)
+    labels = labels.copy()
+    labels[l_off[4] + 7] = 0            # value-0 label -> generic kernel
+    labels[l_off[6] + 3] = 39           # bad label -> status 2
+    info = _compare_batch(kab, lp, t_off, labels, l_off, beam_size=600)
+    assert info.n_class[0] >= 1 and info.n_class[1] >= 2 and info.n_class[2] >= 1
+
+
+@pytest.mark.parametrize("beam_size,max_move", [(1000, 4), (200, 4), (64, 4), (1000, 3), (150, 6)])
+def test_chapter_lattices(kab, beam_size, max_move):
+    """Chapter-shaped banded lattices (band kernel for max_move 4, generic otherwise)."""
+    from kokoro_align_b200 import synth
+    T = np.array([12000, 7001, 3000])
+    L = np.round(0.14 * T).astype(np.int64)
+    lp, t_off, labels, l_off = synth.make_batch(T, L, seed=4000 + beam_size, planted=True)
+    _compare_batch(kab, lp, t_off, labels, l_off, beam_size=beam_size, max_move=max_move)
+
+
+def test_nonfinite_rejected(kab):
+    from kokoro_align_b200 import synth
+    for T, L in ((300, 40), (3000, 900)):
+        lp, labels = synth.make_lattice(T, L, seed=5)
+        lp[T // 2, 7] = -np.inf
+        with pytest.raises(ValueError):
+            kab.ctc_best_path(lp, labels)
+    lp, labels = synth.make_lattice(100, 10, seed=6)
+    lp[99, 38] = np.nan
+    with pytest.raises(ValueError):
+        kab.ctc_best_path(lp, labels, max_move=3)
+
+
+def test_device_resident_torch(kab):
+    """Inputs already in HBM (torch tensors), asynchronous launch on the current stream."""
+    import torch
+    from kokoro_align_b200 import synth
+    from oracle import ctc_oracle
+    T, L = synth.segment_lengths(64, seed=2200)
+    lp, t_off, labels, l_off = synth.make_batch_fast(T, L, seed=2201)
+    rp, rl, rs, rf, rst = ctc_oracle.ctc_best_path_batch(lp, t_off, labels, l_off, n_threads=8)
+    with kab.AlignPlan(t_off, labels, l_off, 39) as plan:
+        d_lp = torch.from_numpy(lp).cuda()
+        path, labs, scores, final, status = plan.run_torch(d_lp)
+        torch.cuda.synchronize()
+    assert (status.cpu().numpy() == 0).all()
+    np.testing.assert_array_equal(path.cpu().numpy(), rp)
+    np.testing.assert_array_equal(labs.cpu().numpy(), rl)
+    assert scores.cpu().numpy().tobytes() == rs.tobytes()
+    assert final.cpu().numpy().tobytes() == rf.tobytes()
+
+
+def test_full_size_properties(kab):
+    """BASELINE config 1 shape (T = 81 135, L = 11 359): size-independent properties plus the
+    C oracle (which finishes this shape in about a second)."""
+    from kokoro_align_b200 import synth
+    from oracle import ctc_oracle
+    T, L = 81135, 11359
+    lp, labels = synth.make_lattice(T, L, seed=1000)
+    path, labs, scores, final = kab.ctc_best_path(lp, labels, return_final_score=True)
+    S = 2 * L + 1
+    d = np.diff(path)
+    assert path[0] in (0, 1, 3) and d.min() >= 0 and d.max() <= 3
+    i = np.arange(T, dtype=np.int64)
+    lo = np.maximum(0, S * i // T - 500)
+    assert (path >= lo).all() and (path < np.minimum(lo + 1000, S)).all()
+    ext = np.zeros(S, np.int32)
+    ext[1::2] = labels
+    np.testing.assert_array_equal(labs, ext[path])
+    assert scores.tobytes() == lp[i, labs].tobytes()
+    assert np.cumsum(scores, dtype=np.float32)[-1].tobytes() == np.float32(final).tobytes()
+    rp, _, _, rf = ctc_oracle.ctc_best_path(lp, labels, return_final_score=True)
+    np.testing.assert_array_equal(path, rp)
+    assert np.float32(final).tobytes() == np.float32(rf).tobytes()
