@@ -60,9 +60,9 @@ class AlignPlan:
         self.info = info
 
     def close(self):
-        if self._h:
-            _lib.lib().kab_plan_destroy(self._h)
-            self._h = ctypes.c_void_p(0)
+        h, self._h = getattr(self, "_h", None), None
+        if h and _lib is not None and _lib._lib is not None:   # (module globals vanish at exit)
+            _lib._lib.kab_plan_destroy(h)
 
     __del__ = close
 

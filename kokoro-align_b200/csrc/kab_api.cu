@@ -152,7 +152,7 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
   pl->sm_count = prop.multiProcessorCount;
 
   // emission staging geometry: ~4 KB stages, at most 16 frames each
-  pl->stage_frames = std::max(1, std::min(16, 4096 / (V * 4)));
+  pl->stage_frames = V <= 64 ? 16 : 8;  // multiple of 8: frame groups never straddle stages
   pl->stage_bytes = (int32_t)align_up((int64_t)pl->stage_frames * V * 4 + 24, 16);
 
   // ---- classify, build the padded column table (numpy-style wrap of negative labels)
@@ -192,9 +192,9 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
     const bool full = W >= S && (S * (T - 1)) / T <= W / 2;
     const int64_t weff = std::min<int64_t>(W, S);
     int q;
-    if (fast && full && S <= 256) {
+    if (fast && full && S <= 248) {
       q = Q_WARP;
-      d.k = S <= 64 ? 2 : (S <= 128 ? 4 : (S <= 192 ? 6 : 8));
+      d.k = S <= 62 ? 2 : (S <= 124 ? 4 : (S <= 186 ? 6 : 8));  // 31 lanes x K states
       const int fpw = d.k <= 2 ? 8 : (d.k <= 4 ? 4 : 2);
       d.bp_off = bp_bytes;
       bp_bytes += align_up((T + fpw - 1) / fpw * 128, 256);
@@ -252,9 +252,10 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
     // ---- launch geometry
     if (!pl->lists[Q_WARP].empty()) {
       const size_t smem = 128 + (size_t)KAB_WARPS_PER_CTA * KAB_WARP_STAGES * pl->stage_bytes;
-      if ((e = cudaFuncSetAttribute(kab_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) { rc = cuda_fail(e, "cudaFuncSetAttribute(warp)"); break; }
+      const void *fn = V == 39 ? (const void *)kab_warp_kernel<39> : (const void *)kab_warp_kernel<0>;
+      if ((e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) { rc = cuda_fail(e, "cudaFuncSetAttribute(warp)"); break; }
       int occ = 0;
-      if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kab_warp_kernel, KAB_WARPS_PER_CTA * 32, smem)) != cudaSuccess) { rc = cuda_fail(e, "occupancy(warp)"); break; }
+      if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, KAB_WARPS_PER_CTA * 32, smem)) != cudaSuccess) { rc = cuda_fail(e, "occupancy(warp)"); break; }
       pl->smem[Q_WARP] = smem;
       const int64_t ctas = ((int64_t)pl->lists[Q_WARP].size() + KAB_WARPS_PER_CTA - 1) / KAB_WARPS_PER_CTA;
       pl->grid[Q_WARP] = (int)std::min<int64_t>(ctas, (int64_t)pl->sm_count * std::max(occ, 1));
@@ -308,8 +309,12 @@ int kab_plan_run_device(kab_plan *pl, const float *d_log_probs, int32_t *d_best_
 
   if (!pl->lists[Q_WARP].empty()) {
     KabParams pw = p; pw.queue = pl->d_queue + Q_WARP;
-    kab_warp_kernel<<<pl->grid[Q_WARP], KAB_WARPS_PER_CTA * 32, pl->smem[Q_WARP], stream>>>(
-        pl->d_lists[Q_WARP], (int)pl->lists[Q_WARP].size(), pw);
+    if (pl->V == 39)
+      kab_warp_kernel<39><<<pl->grid[Q_WARP], KAB_WARPS_PER_CTA * 32, pl->smem[Q_WARP], stream>>>(
+          pl->d_lists[Q_WARP], (int)pl->lists[Q_WARP].size(), pw);
+    else
+      kab_warp_kernel<0><<<pl->grid[Q_WARP], KAB_WARPS_PER_CTA * 32, pl->smem[Q_WARP], stream>>>(
+          pl->d_lists[Q_WARP], (int)pl->lists[Q_WARP].size(), pw);
   }
   for (int b = 0; b < 4; ++b) {
     const int q = Q_BAND0 + b;

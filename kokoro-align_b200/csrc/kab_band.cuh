@@ -85,10 +85,13 @@ __global__ void __launch_bounds__(NT) kab_band_kernel(const KabLattice *__restri
     const uint16_t *col16 = p.col16 + lat.col_off;
     uint32_t *bpw = reinterpret_cast<uint32_t *>(p.bp + lat.bp_off);
 
-    // ---- emission pipeline (thread 0 issues, everybody waits on the stage's mbarrier)
+    // ---- emission pipeline (thread 0 issues, everybody waits on the stage's mbarrier).
+    // Chunk g (counted over the CTA's lifetime) lives in stage g % STAGES and completes phase
+    // (g / STAGES) & 1 of that stage's mbarrier; both are tracked incrementally.
     const uint32_t ec0 = echunks;
-    auto issue = [&](int c) {
-      const uint32_t g = ec0 + c, st = g % KAB_BAND_STAGES;
+    // F*V*4 is a multiple of 16, so every chunk of this lattice has the same 16-byte skew
+    const uint32_t skew = (uint32_t)(((lat.t_off * (int64_t)V * 4) & 15) >> 2);
+    auto issue = [&](int c, uint32_t st) {
       const int f0 = c * F, nf = min(F, T - f0);
       const KabStageDesc d = kab_stage_desc(p, lat.t_off, f0, nf);
       float *dst = stage_base + st * stage_words;
@@ -100,17 +103,8 @@ __global__ void __launch_bounds__(NT) kab_band_kernel(const KabLattice *__restri
       if (tid < (int)d.tail_n)
         dst[d.tail_word + tid] = __ldg(reinterpret_cast<const float *>(d.src) + d.tail_word + tid);
     };
-    auto row_ptr = [&](int i) -> const char * {  // staged row of frame i
-      const int c = i / F;
-      const uint32_t st = (ec0 + c) % KAB_BAND_STAGES;
-      const uint32_t skew = (uint32_t)((((lat.t_off + (int64_t)c * F) * (int64_t)V * 4) & 15) >> 2);
-      return reinterpret_cast<const char *>(stage_base + st * stage_words + skew) + (size_t)(i - c * F) * V * 4;
-    };
-    auto wait_chunk = [&](int c) {
-      const uint32_t g = ec0 + c;
-      kab_mbar_wait(&ebars[g % KAB_BAND_STAGES], (g / KAB_BAND_STAGES) & 1u);
-    };
-    for (int c = 0; c < min(n_chunks, KAB_BAND_STAGES); ++c) issue(c);
+    uint32_t st = ec0 % KAB_BAND_STAGES, ph = (ec0 / KAB_BAND_STAGES) & 1u;  // stage / phase of chunk `cn`
+    for (int c = 0; c < min(n_chunks, KAB_BAND_STAGES); ++c) issue(c, (st + c) % KAB_BAND_STAGES);
 
     // ---- ring init: everything inactive except the virtual start state 0 (align.py:57-58)
     float *prev = ring, *cur = ring + R;
@@ -131,17 +125,19 @@ __global__ void __launch_bounds__(NT) kab_band_kernel(const KabLattice *__restri
     const int half = W / 2;
 
     bool bad = false;
-    wait_chunk(0);
+    kab_mbar_wait(&ebars[st], ph);
     __syncthreads();  // ring init + tail words visible
+    // rowc: staged row whose emissions are in (eb, e1, e3): frame `fin` of chunk `cn`
+    const char *rowc = reinterpret_cast<const char *>(stage_base + st * stage_words + skew);
+    int cn = 0, fin = 0;
     float eb, e1, e3;
-    {
-      const char *rb0 = row_ptr(0);
-      eb = *reinterpret_cast<const float *>(rb0);
-      e1 = *reinterpret_cast<const float *>(rb0 + c1);
-      e3 = *reinterpret_cast<const float *>(rb0 + c3);
-      for (int c = tid; c < V; c += NT) bad |= !kab_finite(reinterpret_cast<const float *>(rb0)[c]);
-    }
+    eb = *reinterpret_cast<const float *>(rowc);
+    e1 = *reinterpret_cast<const float *>(rowc + c1);
+    e3 = *reinterpret_cast<const float *>(rowc + c3);
+    for (int c = tid; c < V; c += NT) bad |= !kab_finite(reinterpret_cast<const float *>(rowc)[c]);
     uint32_t word = 0;
+    int wsh = 0;  // bit position of this frame's byte inside `word`
+    uint32_t *bprow = bpw + tid;
 
     for (int i = 0; i < T; ++i) {
       const int lo = max(0, q - half);  // align.py:64
@@ -151,18 +147,28 @@ __global__ void __launch_bounds__(NT) kab_band_kernel(const KabLattice *__restri
         vb += R;
         c1 = nc1; c3 = nc3;
         load_cols(vb + R, nc1, nc3);
-        const char *rb = row_ptr(i);  // the prefetched emissions belonged to the old alias
-        e1 = *reinterpret_cast<const float *>(rb + c1);
-        e3 = *reinterpret_cast<const float *>(rb + c3);
+        e1 = *reinterpret_cast<const float *>(rowc + c1);  // the prefetched emissions belonged
+        e3 = *reinterpret_cast<const float *>(rowc + c3);  // to the old alias
       }
       const float4 P = *reinterpret_cast<const float4 *>(prev + 4 * tid);
       const float4 H = *reinterpret_cast<const float4 *>(prev + ((4 * tid + R - 4) & (R - 1)));
-      uint32_t m0, m1, m2, m3;
+      // candidates: (even, odd) state pairs share one packed add
+      float t0, t1, t2, t3;
+      kab_add2(P.x, P.y, eb, t0, t1);
+      kab_add2(P.z, P.w, eb, t2, t3);
+      const float th1 = __fadd_rn(H.w, eb), th3 = __fadd_rn(H.y, eb);
+      float a0, a1, a2, a3, b0, b1, b2, b3;
+      kab_add2(P.x, P.y, e1, a1, a0);
+      kab_add2(H.z, H.w, e1, a3, a2);
+      kab_add2(P.z, P.w, e3, b1, b0);
+      kab_add2(P.x, P.y, e3, b3, b2);
+      uint32_t m = 0;
       float4 N;
-      N.x = kab_cell_blank(P.x, H.w, H.y, eb, m0);
-      N.y = kab_cell_label(P.y, P.x, H.w, H.z, e1, m1);
-      N.z = kab_cell_blank(P.z, P.y, H.w, eb, m2);
-      N.w = kab_cell_label(P.w, P.z, P.y, P.x, e3, m3);
+      N.x = kab_blank_sel(t0, th1, th3, m, 1u << 0, 3u << 0);
+      N.y = kab_label_sel(a0, a1, a2, a3, m, 1u << 2, 2u << 2);
+      N.z = kab_blank_sel(t2, t1, th1, m, 1u << 4, 3u << 4);
+      N.w = kab_label_sel(b0, b1, b2, b3, m, 1u << 6, 2u << 6);
+      (void)t3;
       const int nlo = lo - vb, nhi = hi - vb;  // window in chunk coordinates
       if (nlo > 0 || nhi < 4) {                // edge / outside threads only
         if (0 < nlo || 0 >= nhi) N.x = ninf;
@@ -171,37 +177,41 @@ __global__ void __launch_bounds__(NT) kab_band_kernel(const KabLattice *__restri
         if (3 < nlo || 3 >= nhi) N.w = ninf;
       }
       *reinterpret_cast<float4 *>(cur + 4 * tid) = N;
-      word |= (m0 | (m1 << 2) | (m2 << 4) | (m3 << 6)) << (8 * (i & 3));
-      if ((i & 3) == 3) {
-        bpw[(size_t)(i >> 2) * NT + tid] = word;
-        word = 0;
+      word |= m << wsh;
+      wsh += 8;
+      if (wsh == 32) {
+        *bprow = word;
+        bprow += NT;
+        word = 0; wsh = 0;
       }
       // next frame's window and emissions (off the barrier's critical path)
       q += qd; acc += rd;
       if (acc >= T) { acc -= T; ++q; }
-      const int inext = i + 1;
-      if (inext < T) {
-        if (inext % F == 0) {
-          const int c = inext / F;
-          wait_chunk(c);
+      bool crossed = false;
+      if (i + 1 < T) {
+        if (++fin == F) {  // frame i+1 opens chunk cn+1
+          fin = 0; ++cn; crossed = true;
+          if (++st == KAB_BAND_STAGES) { st = 0; ph ^= 1u; }
+          kab_mbar_wait(&ebars[st], ph);
+          rowc = reinterpret_cast<const char *>(stage_base + st * stage_words + skew);
+        } else {
+          rowc += V * 4;
         }
-        const char *rb = row_ptr(inext);
-        eb = *reinterpret_cast<const float *>(rb);
-        e1 = *reinterpret_cast<const float *>(rb + c1);
-        e3 = *reinterpret_cast<const float *>(rb + c3);
-        for (int c = tid; c < V; c += NT) bad |= !kab_finite(reinterpret_cast<const float *>(rb)[c]);
+        eb = *reinterpret_cast<const float *>(rowc);
+        e1 = *reinterpret_cast<const float *>(rowc + c1);
+        e3 = *reinterpret_cast<const float *>(rowc + c3);
+        for (int c = tid; c < V; c += NT) bad |= !kab_finite(reinterpret_cast<const float *>(rowc)[c]);
       }
       __syncthreads();
-      if (inext < T && inext % F == 0) {
-        // every thread has finished with chunk c-1 (its last frame was frame i): refill its
-        // stage with chunk c + STAGES - 1
-        const int c = inext / F;
-        if (c + KAB_BAND_STAGES - 1 < n_chunks) issue(c + KAB_BAND_STAGES - 1);
+      if (crossed && cn + KAB_BAND_STAGES - 1 < n_chunks) {
+        // every thread has finished with chunk cn-1 (its last frame was frame i): refill its
+        // stage (the one before `st`) with chunk cn + STAGES - 1
+        issue(cn + KAB_BAND_STAGES - 1, (st + KAB_BAND_STAGES - 1) % KAB_BAND_STAGES);
       }
-      float *t = prev; prev = cur; cur = t;
+      float *tswap = prev; prev = cur; cur = tswap;
     }
     echunks = ec0 + n_chunks;
-    if (T & 3) bpw[(size_t)(T >> 2) * NT + tid] = word;
+    if (T & 3) *bprow = word;
 
     // ---- forced end state: highest active state of frame T-1 (align.py:99-101)
     {

@@ -136,3 +136,62 @@ __device__ __forceinline__ float kab_cell_label(float s0, float s1, float s2, fl
   mv = ph ? (p23 ? 3u : 2u) : (p01 ? 1u : 0u);
   return ph ? m23 : m01;
 }
+
+// ---------------------------------------------------------------- packed-backpointer cell updates
+// Same arithmetic and tie-break as kab_cell_blank / kab_cell_label, written in PTX:
+//   * the candidate sums come from packed fp32x2 adds (FADD2 on sm_100a: two IEEE-rn fp32 adds,
+//     second operand broadcast), so adjacent states (s[2m], s[2m+1]) share one instruction;
+//   * winners are taken with max.f32 (the candidates are never NaN and never -0, so max returns
+//     exactly the value the reference's first-max argmax selects);
+//   * the 2-bit move goes into the backpointer word with two predicated ORs.
+//     bit1 / bit2 / bit3 are the constants 1 << pos, 2 << pos, 3 << pos.
+__device__ __forceinline__ void kab_add2(float lo, float hi, float e, float &olo, float &ohi) {
+  asm("{\n\t"
+      ".reg .b64 u, v, w;\n\t"
+      "mov.b64 u, {%2, %3};\n\t"
+      "mov.b64 v, {%4, %4};\n\t"
+      "add.rn.f32x2 w, u, v;\n\t"
+      "mov.b64 {%0, %1}, w;\n\t"
+      "}"
+      : "=f"(olo), "=f"(ohi)
+      : "f"(lo), "f"(hi), "f"(e));
+}
+// Blank state: candidates a0 (move 0), a1 (move 1), a3 (move 3); ascending strict-'>' scan.
+__device__ __forceinline__ float kab_blank_sel(float a0, float a1, float a3, uint32_t &w, const uint32_t bit1,
+                                               const uint32_t bit3) {
+  float best;
+  asm("{\n\t"
+      ".reg .f32 m;\n\t"
+      ".reg .pred p1, p3;\n\t"
+      "max.f32 m, %2, %3;\n\t"
+      "setp.gt.f32 p1, %3, %2;\n\t"
+      "setp.gt.f32 p3, %4, m;\n\t"
+      "max.f32 %0, m, %4;\n\t"
+      "@p1 or.b32 %1, %1, %5;\n\t"   // move is 1 unless overridden
+      "@p3 or.b32 %1, %1, %6;\n\t"   // move 3 (1 | 3 == 3)
+      "}"
+      : "=f"(best), "+r"(w)
+      : "f"(a0), "f"(a1), "f"(a3), "r"(bit1), "r"(bit3));
+  return best;
+}
+// Label state: candidates a0..a3; tournament form of the ascending strict-'>' scan: the winner
+// of (0,1) against the winner of (2,3), the upper pair wins only if strictly greater.
+__device__ __forceinline__ float kab_label_sel(float a0, float a1, float a2, float a3, uint32_t &w,
+                                               const uint32_t bit1, const uint32_t bit2) {
+  float best;
+  asm("{\n\t"
+      ".reg .f32 m01, m23, z;\n\t"
+      ".reg .pred ph, pl;\n\t"
+      "max.f32 m01, %2, %3;\n\t"
+      "max.f32 m23, %4, %5;\n\t"
+      "setp.gt.f32 ph, m23, m01;\n\t"
+      "selp.f32 %0, m23, m01, ph;\n\t"
+      "selp.f32 z, %4, %2, ph;\n\t"    // even candidate of the winning pair
+      "setp.gt.f32 pl, %0, z;\n\t"     // low bit: the odd candidate won its pair strictly
+      "@pl or.b32 %1, %1, %6;\n\t"
+      "@ph or.b32 %1, %1, %7;\n\t"     // high bit = ph
+      "}"
+      : "=f"(best), "+r"(w)
+      : "f"(a0), "f"(a1), "f"(a2), "f"(a3), "r"(bit1), "r"(bit2));
+  return best;
+}

@@ -1,18 +1,23 @@
 // kab_warp.cuh -- one WARP per lattice, for the silence-split short segments of BASELINE
-// config 2 (S = 2L+1 <= 256, window never clips: lo_i = 0, hi_i = S for every frame,
+// config 2 (S = 2L+1 <= 248, window never clips: lo_i = 0, hi_i = S for every frame,
 // max_move = 4, labels in 1..V-1, V <= 128).
 //
-//   * state row lives in registers: lane l owns states K*l .. K*l+K-1 (K = 2,4,6,8 even, so
-//     even register index == blank state); the three halo scores come from lane l-1 by
-//     warp shuffle -- no shared-memory round trip and no block barrier on the recurrence.
+//   * state row lives in registers: lane l >= 1 owns states K*(l-1) .. K*l-1 (K = 2,4,6,8 even,
+//     so even register index == blank state; lane 0 is an all -inf dummy that feeds lane 1's
+//     halo); the three halo scores come from lane l-1 by warp shuffle -- no shared-memory round
+//     trip and no block barrier on the recurrence.  Hence S <= 31*K <= 248.
 //   * emission rows (V floats per frame) are staged a few frames ahead into a per-warp
 //     shared-memory ring with 1-D bulk copies (cp.async.bulk + mbarrier complete_tx); the
-//     per-state emission is a conflict-free LDS gather row[col[v]] (V = 39 spans 1.2 banks rows).
-//   * backpointers: 2 bits per cell, packed per lane into 32-bit words (32/BPF frames per
-//     word) and stored as one coalesced 128-byte row per warp: word (i / FPW) * 32 + lane.
-//   * the same warp then backtracks: 16 word-rows are loaded coalesced into registers and the
-//     walk fetches the owner lane's word with a shuffle (no dependent global load per frame);
-//     best_path / best_labels / best_scores leave as coalesced 32-frame stores.
+//     per-state emission is a conflict-free LDS gather row[col[v]] (V = 39 spans 1.2 bank rows).
+//     V = 39 (the reference's vocabulary, encoder.py:11) is a compile-time constant of the
+//     fast instantiation so that the gathers of a frame group use immediate offsets.
+//   * frames are processed in groups of FPW = 32/BPF frames, fully unrolled: one 32-bit word
+//     of 2-bit backpointers per lane and group, stored as one coalesced 128-byte row per warp:
+//     word (i / FPW) * 32 + lane.
+//   * the finiteness check of the log-probs runs once per staged chunk with LDS.128.
+//   * the same warp then backtracks: the word-rows of 32 frames are loaded coalesced into
+//     registers and the walk fetches the owner lane's word with a shuffle (no dependent global
+//     load per frame); best_path / best_labels / best_scores leave as coalesced 32-frame stores.
 //   * warps pull lattices from a global queue sorted by decreasing cost (LPT order).
 #pragma once
 #include "kab_common.cuh"
@@ -26,68 +31,76 @@ struct KabWarpCfg {
   static constexpr int FPW = 32 / BPF;                        // frames per 32-bit word
 };
 
-// One frame of the recurrence for this lane's K states.  s[] holds frame i-1 on entry and
-// frame i on return; returns the 2K backpointer bits of the frame.
+// One frame for this lane's K states; the frame's 2K backpointer bits are OR-ed into w at
+// bits [shift, shift + 2K).  s[] holds frame i-1 on entry and frame i on return.
+// Lane 0 is a dummy whose states are permanently -inf ("states -K..-1"), so the halo of lane 1
+// (state 0's lower neighbours) is -inf without any select.
 template <int K>
-__device__ __forceinline__ uint32_t kab_warp_frame(float (&s)[K], const float eb, const float (&el)[K / 2],
-                                                   const int lane) {
-  const float ninf = kab_neg_inf();
-  float h1, h2, h3;  // scores of states K*lane-1, -2, -3 (previous frame)
+__device__ __forceinline__ void kab_warp_frame(float (&s)[K], const float eb, const float (&el)[K / 2],
+                                               const bool lane1, uint32_t &w, const int shift) {
+  float h1, h2, h3;  // previous-frame scores of states K*(lane-1)-1, -2, -3
   if (K >= 4) {
     h1 = __shfl_up_sync(KAB_FULL_MASK, s[K - 1], 1);
     h2 = __shfl_up_sync(KAB_FULL_MASK, s[K - 2], 1);
     h3 = __shfl_up_sync(KAB_FULL_MASK, s[K >= 4 ? K - 3 : 0], 1);
-    if (lane == 0) { h1 = ninf; h2 = ninf; h3 = ninf; }
   } else {
     h1 = __shfl_up_sync(KAB_FULL_MASK, s[1], 1);
     h2 = __shfl_up_sync(KAB_FULL_MASK, s[0], 1);
     h3 = __shfl_up_sync(KAB_FULL_MASK, s[1], 2);
-    if (lane == 0) { h1 = ninf; h2 = ninf; }
-    if (lane < 2) h3 = ninf;
+    h3 = lane1 ? kab_neg_inf() : h3;  // lane 1: two lanes up is out of range
   }
-  float n[K];
-  uint32_t bits = 0;
+  // blank candidates: t[j] = s[j] + eb for every state (even, odd) pair, plus the halo
+  float t[K];
 #pragma unroll
-  for (int k = 0; k < K; ++k) {
-    // previous-frame score of state (K*lane + k - d)
-    const float s0 = s[k];
-    const float s1 = k >= 1 ? s[k >= 1 ? k - 1 : 0] : h1;
-    const float s2 = k >= 2 ? s[k >= 2 ? k - 2 : 0] : (k == 1 ? h1 : h2);
-    const float s3 = k >= 3 ? s[k >= 3 ? k - 3 : 0] : (k == 2 ? h1 : (k == 1 ? h2 : h3));
-    uint32_t mv;
-    if ((k & 1) == 0) n[k] = kab_cell_blank(s0, s1, s3, eb, mv);
-    else n[k] = kab_cell_label(s0, s1, s2, s3, el[k >> 1], mv);
-    bits |= mv << (2 * k);
+  for (int m = 0; m < K / 2; ++m) kab_add2(s[2 * m], s[2 * m + 1], eb, t[2 * m], t[2 * m + 1]);
+  const float th1 = __fadd_rn(h1, eb), th3 = __fadd_rn(h3, eb);
+  float n[K];
+#pragma unroll
+  for (int q = 0; q < K / 2; ++q) {
+    const int kb = 2 * q, kl = 2 * q + 1;
+    // blank state kb: moves 0, 1, 3
+    const float b1 = kb >= 1 ? t[kb >= 1 ? kb - 1 : 0] : th1;
+    const float b3 = kb >= 3 ? t[kb >= 3 ? kb - 3 : 0] : (kb == 2 ? th1 : th3);
+    n[kb] = kab_blank_sel(t[kb], b1, b3, w, 1u << (shift + 2 * kb), 3u << (shift + 2 * kb));
+    // label state kl: moves 0..3 = states (kl, kl-1) and (kl-2, kl-3), both (even, odd) pairs
+    float a0, a1, a2, a3;
+    kab_add2(s[kl - 1], s[kl], el[q], a1, a0);
+    if (q >= 1) kab_add2(s[q >= 1 ? kl - 3 : 0], s[q >= 1 ? kl - 2 : 0], el[q], a3, a2);
+    else kab_add2(h2, h1, el[q], a3, a2);
+    n[kl] = kab_label_sel(a0, a1, a2, a3, w, 1u << (shift + 2 * kl), 2u << (shift + 2 * kl));
   }
 #pragma unroll
   for (int k = 0; k < K; ++k) s[k] = n[k];
-  return bits;
 }
 
-template <int K>
+// VCT: compile-time vocabulary (39) or 0 = runtime p.V.
+template <int K, int VCT>
 __device__ void kab_warp_align(const KabLattice &lat, const KabParams &p, float *stage_base, uint64_t *bars,
                                uint32_t &chunk_counter, const int lane) {
   using Cfg = KabWarpCfg<K>;
   constexpr int BPF = Cfg::BPF, FPW = Cfg::FPW;
-  const int T = lat.T, S = 2 * lat.L + 1, V = p.V;
-  const int F = p.stage_frames;
+  const int T = lat.T, S = 2 * lat.L + 1;
+  const int V = VCT ? VCT : p.V;
+  const int F = p.stage_frames;  // multiple of 8 (host guarantees), so groups never straddle chunks
   const uint32_t stage_words = p.stage_bytes >> 2;
   const int n_chunks = (T + F - 1) / F;
   const uint16_t *col16 = p.col16 + lat.col_off;
   uint32_t *bpw = reinterpret_cast<uint32_t *>(p.bp + lat.bp_off);
+  const bool lane0 = lane == 0, lane1 = lane == 1;
+  const int sbase = K * (lane - 1);  // first state of this lane (lane 0: dummy, all -inf)
 
   // byte offsets (col * 4) of this lane's K/2 label states inside an emission row
   uint32_t coff[K / 2];
 #pragma unroll
   for (int q = 0; q < K / 2; ++q) {
-    const int v = K * lane + 2 * q + 1;
-    coff[q] = v < S ? 4u * col16[(v - 1) >> 1] : 0u;
+    const int v = sbase + 2 * q + 1;
+    coff[q] = (v > 0 && v < S) ? 4u * col16[(v - 1) >> 1] : 0u;
   }
 
   float s[K];
 #pragma unroll
   for (int k = 0; k < K; ++k) s[k] = kab_neg_inf();
-  if (lane == 0) s[0] = 0.0f;  // virtual start state 0, score 0 (align.py:57-58)
+  if (lane1) s[0] = 0.0f;  // virtual start state 0, score 0 (align.py:57-58)
 
   // -- emission pipeline: chunk c uses stage (chunk_counter + c) % STAGES
   const uint32_t cc0 = chunk_counter;
@@ -96,7 +109,7 @@ __device__ void kab_warp_align(const KabLattice &lat, const KabParams &p, float 
     const int f0 = c * F, nf = min(F, T - f0);
     const KabStageDesc d = kab_stage_desc(p, lat.t_off, f0, nf);
     float *dst = stage_base + st * stage_words;
-    if (lane == 0) {
+    if (lane0) {
       kab_mbar_expect_tx(&bars[st], d.bytes);
       if (d.bytes) kab_bulk_g2s(dst, d.src, d.bytes, &bars[st]);
     }
@@ -107,8 +120,7 @@ __device__ void kab_warp_align(const KabLattice &lat, const KabParams &p, float 
   for (int c = 0; c < pre; ++c) issue(c);
 
   bool bad = false;
-  uint32_t word = 0;
-  int i = 0;
+  uint32_t *bprow = bpw + lane;  // this lane's slot in the current word-row
   for (int c = 0; c < n_chunks; ++c) {
     // the stage consumed in iteration c-1 is free again: refill it with chunk c + STAGES - 1
     __syncwarp();
@@ -120,34 +132,58 @@ __device__ void kab_warp_align(const KabLattice &lat, const KabParams &p, float 
     kab_mbar_wait(&bars[st], (g / KAB_WARP_STAGES) & 1u);
     __syncwarp();
     const int f0 = c * F, nf = min(F, T - f0);
-    const uint32_t skew = (uint32_t)((((lat.t_off + f0) * (int64_t)V * 4) & 15) >> 2);
-    const char *rowb = reinterpret_cast<const char *>(stage_base + st * stage_words + skew);
-    for (int f = 0; f < nf; ++f, ++i, rowb += V * 4) {
-      const float *row = reinterpret_cast<const float *>(rowb);
-      for (int cidx = lane; cidx < V; cidx += 32) bad |= !kab_finite(row[cidx]);
-      const float eb = row[0];
-      float el[K / 2];
-#pragma unroll
-      for (int q = 0; q < K / 2; ++q) el[q] = *reinterpret_cast<const float *>(rowb + coff[q]);
-      const uint32_t bits = kab_warp_frame<K>(s, eb, el, lane);
-      const int sub = i % FPW;
-      word |= bits << (sub * BPF);
-      if (sub == FPW - 1) {
-        bpw[(size_t)(i / FPW) * 32 + lane] = word;
-        word = 0;
+    const float *stage = stage_base + st * stage_words;
+    const int w0 = (int)((((lat.t_off + f0) * (int64_t)V * 4) & 15) >> 2), w1 = w0 + nf * V;
+    {  // finiteness of exactly this lattice's words [w0, w1) of the stage
+      const int v0 = (w0 + 3) >> 2, v1 = w1 >> 2;
+      const float4 *s4 = reinterpret_cast<const float4 *>(stage);
+      for (int j = v0 + lane; j < v1; j += 32) {
+        const float4 x = s4[j];
+        bad |= !(kab_finite(x.x) && kab_finite(x.y) && kab_finite(x.z) && kab_finite(x.w));
       }
+      if (lane < 4 * v0 - w0 && w0 + lane < w1) bad |= !kab_finite(stage[w0 + lane]);
+      if (4 * v1 >= w0 && lane < w1 - 4 * v1) bad |= !kab_finite(stage[4 * v1 + lane]);
+    }
+    const char *rowb = reinterpret_cast<const char *>(stage + w0);
+    const int n_groups = nf / FPW;
+    for (int gi = 0; gi < n_groups; ++gi, rowb += FPW * V * 4) {
+      uint32_t word = 0;
+#pragma unroll
+      for (int f = 0; f < FPW; ++f) {
+        const char *rb = rowb + f * V * 4;
+        const float eb = *reinterpret_cast<const float *>(rb);
+        float el[K / 2];
+#pragma unroll
+        for (int q = 0; q < K / 2; ++q) el[q] = *reinterpret_cast<const float *>(rb + coff[q]);
+        kab_warp_frame<K>(s, eb, el, lane1, word, f * BPF);
+      }
+      *bprow = word;
+      bprow += 32;
+    }
+    const int rem = nf - n_groups * FPW;  // only in the last chunk
+    if (rem) {
+      uint32_t word = 0;
+      for (int f = 0; f < rem; ++f, rowb += V * 4) {
+        const float eb = *reinterpret_cast<const float *>(rowb);
+        float el[K / 2];
+#pragma unroll
+        for (int q = 0; q < K / 2; ++q) el[q] = *reinterpret_cast<const float *>(rowb + coff[q]);
+        uint32_t fw = 0;
+        kab_warp_frame<K>(s, eb, el, lane1, fw, 0);
+        word |= fw << (f * BPF);
+      }
+      *bprow = word;
     }
   }
   chunk_counter = cc0 + n_chunks;
-  if (T % FPW) bpw[(size_t)(T / FPW) * 32 + lane] = word;
   __syncwarp();
 
   // -- forced end state: highest active state of frame T-1 (align.py:99-101)
   int cand = -1;
 #pragma unroll
   for (int k = 0; k < K; ++k) {
-    const int v = K * lane + k;
-    if (v < S && s[k] > kab_neg_inf()) cand = v;
+    const int v = sbase + k;
+    if (v >= 0 && v < S && s[k] > kab_neg_inf()) cand = v;
   }
   int v = __reduce_max_sync(KAB_FULL_MASK, cand);
   const bool any_bad = __any_sync(KAB_FULL_MASK, bad);
@@ -158,53 +194,54 @@ __device__ void kab_warp_align(const KabLattice &lat, const KabParams &p, float 
       float mine = s[0];
 #pragma unroll
       for (int k = 1; k < K; ++k) if (k == v % K) mine = s[k];
-      fs = __shfl_sync(KAB_FULL_MASK, mine, v / K);
+      fs = __shfl_sync(KAB_FULL_MASK, mine, v / K + 1);
     }
-    if (lane == 0) {
+    if (lane0) {
       p.status[lat.index] = status;
       if (p.final_score) p.final_score[lat.index] = fs;
     }
   }
   if (status != 0) return;
 
-  // -- backtrack (== flush_determined_path, align.py:21-40), 16 word-rows per block
-  const int n_rows = (T + FPW - 1) / FPW;
+  // -- backtrack (== flush_determined_path, align.py:21-40), 32 frames (RPB word-rows) per block
+  constexpr int RPB = 32 / FPW;
   int32_t *out_path = p.best_path + lat.t_off;
   int32_t *out_lab = p.best_labels + lat.t_off;
   float *out_sc = p.best_scores + lat.t_off;
   const float *lp = p.lp + lat.t_off * (int64_t)V;
-  int myv = 0;
-  for (int rb = ((n_rows - 1) / 16) * 16; rb >= 0; rb -= 16) {
-    uint32_t wr[16];
+  const int n_rows = (T + FPW - 1) / FPW;
+  for (int fb = ((T - 1) >> 5) << 5; fb >= 0; fb -= 32) {  // frames fb .. fb+31
+    const int rb = fb / FPW;
+    uint32_t wr[RPB];
 #pragma unroll
-    for (int r = 0; r < 16; ++r)
+    for (int r = 0; r < RPB; ++r)
       wr[r] = (rb + r) < n_rows ? __ldcg(&bpw[(size_t)(rb + r) * 32 + lane]) : 0u;
+    int myv = 0;
 #pragma unroll
-    for (int r = 15; r >= 0; --r) {
+    for (int r = RPB - 1; r >= 0; --r) {
 #pragma unroll
       for (int f = FPW - 1; f >= 0; --f) {
-        const int fi = (rb + r) * FPW + f;  // frame index (warp-uniform)
-        if (fi < T) {
+        const int fl = r * FPW + f;  // frame fb + fl is held by lane fl
+        if (fb + fl < T) {
           const int owner = v / K, k = v - owner * K;
-          const uint32_t w = __shfl_sync(KAB_FULL_MASK, wr[r], owner);
+          const uint32_t w = __shfl_sync(KAB_FULL_MASK, wr[r], owner + 1);
           const uint32_t mv = (w >> (f * BPF + 2 * k)) & 3u;
-          if (lane == (fi & 31)) myv = v;
+          if (lane == fl) myv = v;
           v -= (int)mv;
         }
-        if ((fi & 31) == 0) {  // lanes now hold frames fi .. fi+31
-          const int t = fi + lane;
-          if (t < T) {
-            const int lab = (myv & 1) ? (int)col16[(myv - 1) >> 1] : 0;
-            out_path[t] = myv;
-            out_lab[t] = lab;                              // align.py:106
-            out_sc[t] = __ldg(&lp[(int64_t)t * V + lab]);  // align.py:107
-          }
-        }
       }
+    }
+    const int t = fb + lane;
+    if (t < T) {
+      const int lab = (myv & 1) ? (int)col16[(myv - 1) >> 1] : 0;
+      out_path[t] = myv;
+      out_lab[t] = lab;                              // align.py:106
+      out_sc[t] = __ldg(&lp[(int64_t)t * V + lab]);  // align.py:107
     }
   }
 }
 
+template <int VCT>
 __global__ void __launch_bounds__(KAB_WARPS_PER_CTA * 32)
     kab_warp_kernel(const KabLattice *__restrict__ lats, int n_lat, KabParams p) {
   extern __shared__ __align__(128) unsigned char kab_smem[];
@@ -225,10 +262,10 @@ __global__ void __launch_bounds__(KAB_WARPS_PER_CTA * 32)
     if (item >= (unsigned int)n_lat) break;
     const KabLattice lat = lats[item];
     switch (lat.k) {
-      case 2: kab_warp_align<2>(lat, p, stage_base, bars, chunk_counter, lane); break;
-      case 4: kab_warp_align<4>(lat, p, stage_base, bars, chunk_counter, lane); break;
-      case 6: kab_warp_align<6>(lat, p, stage_base, bars, chunk_counter, lane); break;
-      default: kab_warp_align<8>(lat, p, stage_base, bars, chunk_counter, lane); break;
+      case 2: kab_warp_align<2, VCT>(lat, p, stage_base, bars, chunk_counter, lane); break;
+      case 4: kab_warp_align<4, VCT>(lat, p, stage_base, bars, chunk_counter, lane); break;
+      case 6: kab_warp_align<6, VCT>(lat, p, stage_base, bars, chunk_counter, lane); break;
+      default: kab_warp_align<8, VCT>(lat, p, stage_base, bars, chunk_counter, lane); break;
     }
     __syncwarp();
   }
