@@ -223,8 +223,11 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
   // longest-processing-time-first order inside every queue
   for (int q = 0; q < N_QUEUES; ++q)
     std::stable_sort(pl->lists[q].begin(), pl->lists[q].end(), [&](const KabLattice &a, const KabLattice &b2) {
-      const int64_t ca = (int64_t)a.T * (q == Q_WARP ? a.k : 1), cb = (int64_t)b2.T * (q == Q_WARP ? b2.k : 1);
-      return ca > cb;
+      // warp class: K-major (warps resident on one SM then run the same code variant, which
+      // keeps the instruction cache warm), longest first inside each K and the cheap K = 2
+      // lattices last, where they fill the tail
+      if (q == Q_WARP && a.k != b2.k) return a.k > b2.k;
+      return a.T > b2.T;
     });
 
   // ---- device allocations
@@ -302,6 +305,7 @@ int kab_plan_run_device(kab_plan *pl, const float *d_log_probs, int32_t *d_best_
   p.final_score = d_final_score; p.status = d_status;
   p.V = pl->V; p.W = pl->W; p.M = pl->M;
   p.stage_frames = pl->stage_frames; p.stage_bytes = pl->stage_bytes;
+  p.one = 1u;
 
   KAB_CUDA(cudaMemsetAsync(pl->d_queue, 0, N_QUEUES * sizeof(unsigned int), stream));
   if (pl->any_bad_label)

@@ -125,6 +125,7 @@ __global__ void __launch_bounds__(NT) kab_band_kernel(const KabLattice *__restri
     const int half = W / 2;
 
     bool bad = false;
+    const uint32_t one = p.one;  // runtime 1 (see kab_blank_sel)
     kab_mbar_wait(&ebars[st], ph);
     __syncthreads();  // ring init + tail words visible
     // rowc: staged row whose emissions are in (eb, e1, e3): frame `fin` of chunk `cn`
@@ -164,10 +165,10 @@ __global__ void __launch_bounds__(NT) kab_band_kernel(const KabLattice *__restri
       kab_add2(P.x, P.y, e3, b3, b2);
       uint32_t m = 0;
       float4 N;
-      N.x = kab_blank_sel(t0, th1, th3, m, 1u << 0, 3u << 0);
-      N.y = kab_label_sel(a0, a1, a2, a3, m, 1u << 2, 2u << 2);
-      N.z = kab_blank_sel(t2, t1, th1, m, 1u << 4, 3u << 4);
-      N.w = kab_label_sel(b0, b1, b2, b3, m, 1u << 6, 2u << 6);
+      N.x = kab_blank_sel(t0, th1, th3, m, 1u << 0, 2u << 0, one);
+      N.y = kab_label_sel(a0, a1, a2, a3, m, 1u << 2, 2u << 2, one);
+      N.z = kab_blank_sel(t2, t1, th1, m, 1u << 4, 2u << 4, one);
+      N.w = kab_label_sel(b0, b1, b2, b3, m, 1u << 6, 2u << 6, one);
       (void)t3;
       const int nlo = lo - vb, nhi = hi - vb;  // window in chunk coordinates
       if (nlo > 0 || nhi < 4) {                // edge / outside threads only
@@ -263,7 +264,7 @@ __global__ void __launch_bounds__(NT) kab_band_kernel(const KabLattice *__restri
             const int slot = v & (R - 1);
             const unsigned char byte = blkp[(((i - i0) >> 2) * NT + (slot >> 2)) * 4 + (i & 3)];
             pathbuf[i - i0] = v;
-            v -= (byte >> (2 * (slot & 3))) & 3;
+            v -= kab_decode_move((byte >> (2 * (slot & 3))) & 3u, v);
           }
         }
         __syncthreads();

@@ -40,6 +40,7 @@ struct KabParams {
   int32_t V, W, M;
   int32_t stage_frames;     // emission frames per bulk-copy stage
   int32_t stage_bytes;      // bytes of one stage buffer (multiple of 16)
+  uint32_t one;             // the value 1, opaque to the compiler (kab_blank_sel / kab_label_sel)
 };
 
 __device__ __forceinline__ float kab_neg_inf() { return __int_as_float(0xff800000); }
@@ -144,7 +145,7 @@ __device__ __forceinline__ float kab_cell_label(float s0, float s1, float s2, fl
 //   * winners are taken with max.f32 (the candidates are never NaN and never -0, so max returns
 //     exactly the value the reference's first-max argmax selects);
 //   * the 2-bit move goes into the backpointer word with two predicated ORs.
-//     bit1 / bit2 / bit3 are the constants 1 << pos, 2 << pos, 3 << pos.
+//     bit1 / bit2 are the constants 1 << pos, 2 << pos.
 __device__ __forceinline__ void kab_add2(float lo, float hi, float e, float &olo, float &ohi) {
   asm("{\n\t"
       ".reg .b64 u, v, w;\n\t"
@@ -157,8 +158,17 @@ __device__ __forceinline__ void kab_add2(float lo, float hi, float e, float &olo
       : "f"(lo), "f"(hi), "f"(e));
 }
 // Blank state: candidates a0 (move 0), a1 (move 1), a3 (move 3); ascending strict-'>' scan.
+// The predicated "OR" is issued as mad.lo (w = one * bit + w, `one` is a register holding 1 that
+// ptxas cannot fold): IMAD runs on the FMA pipe, the compares/max/selects on the ALU pipe, and
+// both pipes issue at half rate on sm_100 -- this keeps them balanced.  The bits touched by one
+// frame are disjoint, so the adds never carry.
+// Blank-state code: bit 0 = (move 1 beat move 0), bit 1 = (move 3 beat both); decode with
+// kab_decode_move: code >= 2 -> move 3, else move = code.  Label-state code == move.
+__device__ __forceinline__ int kab_decode_move(uint32_t code, int v) {
+  return ((v & 1) == 0 && code >= 2u) ? 3 : (int)code;
+}
 __device__ __forceinline__ float kab_blank_sel(float a0, float a1, float a3, uint32_t &w, const uint32_t bit1,
-                                               const uint32_t bit3) {
+                                               const uint32_t bit2, const uint32_t one) {
   float best;
   asm("{\n\t"
       ".reg .f32 m;\n\t"
@@ -167,17 +177,17 @@ __device__ __forceinline__ float kab_blank_sel(float a0, float a1, float a3, uin
       "setp.gt.f32 p1, %3, %2;\n\t"
       "setp.gt.f32 p3, %4, m;\n\t"
       "max.f32 %0, m, %4;\n\t"
-      "@p1 or.b32 %1, %1, %5;\n\t"   // move is 1 unless overridden
-      "@p3 or.b32 %1, %1, %6;\n\t"   // move 3 (1 | 3 == 3)
+      "@p1 mad.lo.u32 %1, %7, %5, %1;\n\t"   // code bit 0: move 1 beat move 0
+      "@p3 mad.lo.u32 %1, %7, %6, %1;\n\t"   // code bit 1: move 3 beat both (bit 0 is then don't-care)
       "}"
       : "=f"(best), "+r"(w)
-      : "f"(a0), "f"(a1), "f"(a3), "r"(bit1), "r"(bit3));
+      : "f"(a0), "f"(a1), "f"(a3), "r"(bit1), "r"(bit2), "r"(one));
   return best;
 }
 // Label state: candidates a0..a3; tournament form of the ascending strict-'>' scan: the winner
 // of (0,1) against the winner of (2,3), the upper pair wins only if strictly greater.
 __device__ __forceinline__ float kab_label_sel(float a0, float a1, float a2, float a3, uint32_t &w,
-                                               const uint32_t bit1, const uint32_t bit2) {
+                                               const uint32_t bit1, const uint32_t bit2, const uint32_t one) {
   float best;
   asm("{\n\t"
       ".reg .f32 m01, m23, z;\n\t"
@@ -188,10 +198,10 @@ __device__ __forceinline__ float kab_label_sel(float a0, float a1, float a2, flo
       "selp.f32 %0, m23, m01, ph;\n\t"
       "selp.f32 z, %4, %2, ph;\n\t"    // even candidate of the winning pair
       "setp.gt.f32 pl, %0, z;\n\t"     // low bit: the odd candidate won its pair strictly
-      "@pl or.b32 %1, %1, %6;\n\t"
-      "@ph or.b32 %1, %1, %7;\n\t"     // high bit = ph
+      "@pl mad.lo.u32 %1, %8, %6, %1;\n\t"
+      "@ph mad.lo.u32 %1, %8, %7, %1;\n\t"     // high bit = ph
       "}"
       : "=f"(best), "+r"(w)
-      : "f"(a0), "f"(a1), "f"(a2), "f"(a3), "r"(bit1), "r"(bit2));
+      : "f"(a0), "f"(a1), "f"(a2), "f"(a3), "r"(bit1), "r"(bit2), "r"(one));
   return best;
 }

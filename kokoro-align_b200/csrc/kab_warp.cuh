@@ -37,7 +37,8 @@ struct KabWarpCfg {
 // (state 0's lower neighbours) is -inf without any select.
 template <int K>
 __device__ __forceinline__ void kab_warp_frame(float (&s)[K], const float eb, const float (&el)[K / 2],
-                                               const bool lane1, uint32_t &w, const int shift) {
+                                               const bool lane1, uint32_t &w, const int shift,
+                                               const uint32_t one) {
   float h1, h2, h3;  // previous-frame scores of states K*(lane-1)-1, -2, -3
   if (K >= 4) {
     h1 = __shfl_up_sync(KAB_FULL_MASK, s[K - 1], 1);
@@ -61,13 +62,13 @@ __device__ __forceinline__ void kab_warp_frame(float (&s)[K], const float eb, co
     // blank state kb: moves 0, 1, 3
     const float b1 = kb >= 1 ? t[kb >= 1 ? kb - 1 : 0] : th1;
     const float b3 = kb >= 3 ? t[kb >= 3 ? kb - 3 : 0] : (kb == 2 ? th1 : th3);
-    n[kb] = kab_blank_sel(t[kb], b1, b3, w, 1u << (shift + 2 * kb), 3u << (shift + 2 * kb));
+    n[kb] = kab_blank_sel(t[kb], b1, b3, w, 1u << (shift + 2 * kb), 2u << (shift + 2 * kb), one);
     // label state kl: moves 0..3 = states (kl, kl-1) and (kl-2, kl-3), both (even, odd) pairs
     float a0, a1, a2, a3;
     kab_add2(s[kl - 1], s[kl], el[q], a1, a0);
     if (q >= 1) kab_add2(s[q >= 1 ? kl - 3 : 0], s[q >= 1 ? kl - 2 : 0], el[q], a3, a2);
     else kab_add2(h2, h1, el[q], a3, a2);
-    n[kl] = kab_label_sel(a0, a1, a2, a3, w, 1u << (shift + 2 * kl), 2u << (shift + 2 * kl));
+    n[kl] = kab_label_sel(a0, a1, a2, a3, w, 1u << (shift + 2 * kl), 2u << (shift + 2 * kl), one);
   }
 #pragma unroll
   for (int k = 0; k < K; ++k) s[k] = n[k];
@@ -87,6 +88,7 @@ __device__ void kab_warp_align(const KabLattice &lat, const KabParams &p, float 
   const uint16_t *col16 = p.col16 + lat.col_off;
   uint32_t *bpw = reinterpret_cast<uint32_t *>(p.bp + lat.bp_off);
   const bool lane0 = lane == 0, lane1 = lane == 1;
+  const uint32_t one = p.one;  // runtime 1 (see kab_blank_sel)
   const int sbase = K * (lane - 1);  // first state of this lane (lane 0: dummy, all -inf)
 
   // byte offsets (col * 4) of this lane's K/2 label states inside an emission row
@@ -124,10 +126,9 @@ __device__ void kab_warp_align(const KabLattice &lat, const KabParams &p, float 
   for (int c = 0; c < n_chunks; ++c) {
     // the stage consumed in iteration c-1 is free again: refill it with chunk c + STAGES - 1
     __syncwarp();
-    if (c + KAB_WARP_STAGES - 1 < n_chunks) {
-      kab_fence_proxy_async();
-      issue(c + KAB_WARP_STAGES - 1);
-    }
+    // (every LDS of that stage has completed: its values were consumed by the frame updates
+    // this warp has already issued, so the bulk copy cannot overtake a pending read)
+    if (c + KAB_WARP_STAGES - 1 < n_chunks) issue(c + KAB_WARP_STAGES - 1);
     const uint32_t g = cc0 + c, st = g % KAB_WARP_STAGES;
     kab_mbar_wait(&bars[st], (g / KAB_WARP_STAGES) & 1u);
     __syncwarp();
@@ -155,7 +156,7 @@ __device__ void kab_warp_align(const KabLattice &lat, const KabParams &p, float 
         float el[K / 2];
 #pragma unroll
         for (int q = 0; q < K / 2; ++q) el[q] = *reinterpret_cast<const float *>(rb + coff[q]);
-        kab_warp_frame<K>(s, eb, el, lane1, word, f * BPF);
+        kab_warp_frame<K>(s, eb, el, lane1, word, f * BPF, one);
       }
       *bprow = word;
       bprow += 32;
@@ -163,13 +164,14 @@ __device__ void kab_warp_align(const KabLattice &lat, const KabParams &p, float 
     const int rem = nf - n_groups * FPW;  // only in the last chunk
     if (rem) {
       uint32_t word = 0;
+#pragma unroll 1
       for (int f = 0; f < rem; ++f, rowb += V * 4) {
         const float eb = *reinterpret_cast<const float *>(rowb);
         float el[K / 2];
 #pragma unroll
         for (int q = 0; q < K / 2; ++q) el[q] = *reinterpret_cast<const float *>(rowb + coff[q]);
         uint32_t fw = 0;
-        kab_warp_frame<K>(s, eb, el, lane1, fw, 0);
+        kab_warp_frame<K>(s, eb, el, lane1, fw, 0, one);
         word |= fw << (f * BPF);
       }
       *bprow = word;
@@ -203,40 +205,44 @@ __device__ void kab_warp_align(const KabLattice &lat, const KabParams &p, float 
   }
   if (status != 0) return;
 
-  // -- backtrack (== flush_determined_path, align.py:21-40), 32 frames (RPB word-rows) per block
-  constexpr int RPB = 32 / FPW;
+  // -- backtrack (== flush_determined_path, align.py:21-40).  Word-rows are fetched four at a
+  // time (coalesced 128-byte rows, L2-resident: this warp wrote them moments ago), the walk
+  // reads the owner lane's word by shuffle, and every 32 frames the lanes flush one coalesced
+  // row of each output array.
+  constexpr int RB = 4;  // word-rows per block
   int32_t *out_path = p.best_path + lat.t_off;
   int32_t *out_lab = p.best_labels + lat.t_off;
   float *out_sc = p.best_scores + lat.t_off;
   const float *lp = p.lp + lat.t_off * (int64_t)V;
   const int n_rows = (T + FPW - 1) / FPW;
-  for (int fb = ((T - 1) >> 5) << 5; fb >= 0; fb -= 32) {  // frames fb .. fb+31
-    const int rb = fb / FPW;
-    uint32_t wr[RPB];
+  int myv = 0;
+  for (int rb = ((n_rows - 1) / RB) * RB; rb >= 0; rb -= RB) {
+    uint32_t wr[RB];
 #pragma unroll
-    for (int r = 0; r < RPB; ++r)
+    for (int r = 0; r < RB; ++r)
       wr[r] = (rb + r) < n_rows ? __ldcg(&bpw[(size_t)(rb + r) * 32 + lane]) : 0u;
-    int myv = 0;
 #pragma unroll
-    for (int r = RPB - 1; r >= 0; --r) {
+    for (int r = RB - 1; r >= 0; --r) {
 #pragma unroll
       for (int f = FPW - 1; f >= 0; --f) {
-        const int fl = r * FPW + f;  // frame fb + fl is held by lane fl
-        if (fb + fl < T) {
+        const int fi = (rb + r) * FPW + f;  // frame index (warp-uniform)
+        if (fi < T) {
           const int owner = v / K, k = v - owner * K;
           const uint32_t w = __shfl_sync(KAB_FULL_MASK, wr[r], owner + 1);
-          const uint32_t mv = (w >> (f * BPF + 2 * k)) & 3u;
-          if (lane == fl) myv = v;
-          v -= (int)mv;
+          if (lane == (fi & 31)) myv = v;
+          v -= kab_decode_move((w >> (f * BPF + 2 * k)) & 3u, v);
         }
       }
     }
-    const int t = fb + lane;
-    if (t < T) {
-      const int lab = (myv & 1) ? (int)col16[(myv - 1) >> 1] : 0;
-      out_path[t] = myv;
-      out_lab[t] = lab;                              // align.py:106
-      out_sc[t] = __ldg(&lp[(int64_t)t * V + lab]);  // align.py:107
+    const int fb = rb * FPW;  // first frame of the block; lanes hold frames (fb & ~31) .. +31
+    if ((fb & 31) == 0) {
+      const int t = fb + lane;
+      if (t < T) {
+        const int lab = (myv & 1) ? (int)col16[(myv - 1) >> 1] : 0;
+        out_path[t] = myv;
+        out_lab[t] = lab;                              // align.py:106
+        out_sc[t] = __ldg(&lp[(int64_t)t * V + lab]);  // align.py:107
+      }
     }
   }
 }
