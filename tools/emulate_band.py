@@ -30,6 +30,9 @@ def label(s0, s1, s2, s3, e):
 
 
 def band_emulate(lp, labels, W, NT):
+    """Event-driven variant (kab_band.cuh v2): threads know nothing about the window except at
+    their own event frames, where they recompute lo/hi exactly, recycle their chunk, refresh
+    the per-cell caps (+inf inside the window, -inf outside) and schedule their next event."""
     T, V = lp.shape
     L = len(labels)
     S = 2 * L + 1
@@ -40,25 +43,44 @@ def band_emulate(lp, labels, W, NT):
     prev = np.full(R, NINF, np.float32)
     prev[0] = 0
     vb = 4 * tid
+    half = W // 2
+    caps = np.full((NT, 4), NINF, np.float32)
+    next_event = np.zeros(NT, np.int64)
+    BIG = 1 << 62
+    n_events = 0
 
     def cols(base):
         c1 = np.where(base + 1 < S, col[np.minimum(base >> 1, len(col) - 2)], 0)
         c3 = np.where(base + 3 < S, col[np.minimum((base >> 1) + 1, len(col) - 1)], 0)
         return c1, c3
+
+    def handle_event(t, i):
+        lo = max(0, S * i // T - half)
+        hi = min(lo + W, S)
+        while vb[t] + 3 < lo - 3:
+            vb[t] += R
+        for k in range(4):
+            v = vb[t] + k
+            caps[t, k] = np.float32(np.inf) if lo <= v < hi else NINF
+        # next lo value at which this thread's pattern changes
+        th = [vb[t] + 1, vb[t] + 2, vb[t] + 3, vb[t] + 4, vb[t] + 7]
+        th += [vb[t] + k - W + 1 for k in range(4) if vb[t] + k < S]
+        th = [x for x in th if x > lo]
+        if not th:
+            return BIG
+        Lstar = min(th)
+        # first frame with lo_i >= Lstar  <=>  floor(S*i/T) >= Lstar + half
+        need = Lstar + half
+        return -((-need * T) // S)   # ceil(need*T/S)
+
     c1, c3 = cols(vb)
-    qd, rd = S // T, S % T
-    q = acc = 0
-    half = W // 2
     bp = np.zeros((T, NT), np.uint8)
     with np.errstate(invalid="ignore"):
         for i in range(T):
-            lo = max(0, q - half)
-            hi = min(lo + W, S)
-            assert lo == max(0, S * i // T - W // 2)
-            rec = vb + 3 < lo - 3
-            while rec.any():
-                vb = np.where(rec, vb + R, vb)
-                rec = vb + 3 < lo - 3
+            for t in np.nonzero(next_event == i)[0]:
+                next_event[t] = handle_event(t, i)
+                assert next_event[t] > i
+                n_events += 1
             c1, c3 = cols(vb)
             row = lp[i]
             eb, e1, e3 = row[0], row[c1], row[c3]
@@ -69,16 +91,9 @@ def band_emulate(lp, labels, W, NT):
             n2, m2 = blank(P[:, 2], P[:, 1], H[:, 3], eb)
             n3, m3 = label(P[:, 3], P[:, 2], P[:, 1], P[:, 0], e3)
             N = np.stack([n0, n1, n2, n3], 1).astype(np.float32)
-            nlo, nhi = lo - vb, hi - vb
-            k = np.arange(4)[None, :]
-            N = np.where((k < nlo[:, None]) | (k >= nhi[:, None]), NINF, N)
+            N = np.minimum(N, caps)
             bp[i] = m0 | (m1 << 2) | (m2 << 4) | (m3 << 6)
             prev = N.reshape(-1).copy()
-            q += qd
-            acc += rd
-            if acc >= T:
-                acc -= T
-                q += 1
     states = vb[:, None] + np.arange(4)[None, :]
     ok = (states < S) & (prev.reshape(NT, 4) > NINF)
     if not ok.any():
@@ -90,6 +105,7 @@ def band_emulate(lp, labels, W, NT):
         slot = v % R
         path[i] = v
         v -= (int(bp[i, slot >> 2]) >> (2 * (slot & 3))) & 3
+    band_emulate.events = n_events
     return path, final
 
 
@@ -121,7 +137,7 @@ def main():
             assert np.array_equal(ref[0], got[0]), (trial, NT, W, T, L)
             assert np.float32(ref[1]).tobytes() == np.float32(got[1]).tobytes()
         n += 1
-    print(f"band ring emulation == oracle on {n} random cases")
+    print(f"band ring emulation (event-driven) == oracle on {n} random cases")
 
 
 if __name__ == "__main__":
