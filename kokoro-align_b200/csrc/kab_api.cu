@@ -73,6 +73,16 @@ struct kab_plan {
   // launch geometry
   int grid[N_QUEUES] = {};
   size_t smem[N_QUEUES] = {};
+  // host copies (used to build the pipelined segments of kab_plan_run_host)
+  std::vector<int64_t> h_t_off, h_l_off;
+  std::vector<int32_t> h_labels;
+  // kab_plan_run_host: the batch is cut into contiguous segments (child plans) so that the
+  // H2D copy of segment k+1, the kernels of segment k and the D2H copy of segment k-1 overlap
+  std::vector<kab_plan *> segs;
+  std::vector<int64_t> seg_b0;
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  std::vector<cudaEvent_t> ev_in, ev_cmp;
+  bool is_child = false;
   // buffers of kab_plan_run_host
   cudaStream_t stream = nullptr;
   float *d_lp = nullptr;
@@ -102,6 +112,11 @@ int plan_free(kab_plan *pl) {
   cudaFree(pl->d_lp); cudaFree(pl->d_path); cudaFree(pl->d_lab); cudaFree(pl->d_st);
   cudaFree(pl->d_sc); cudaFree(pl->d_fs);
   if (pl->stream) cudaStreamDestroy(pl->stream);
+  if (pl->s_in) cudaStreamDestroy(pl->s_in);
+  if (pl->s_out) cudaStreamDestroy(pl->s_out);
+  for (cudaEvent_t e : pl->ev_in) cudaEventDestroy(e);
+  for (cudaEvent_t e : pl->ev_cmp) cudaEventDestroy(e);
+  for (kab_plan *c : pl->segs) plan_free(c);
   delete pl;
   return KAB_OK;
 }
@@ -146,6 +161,11 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
   pl->device = device; pl->B = B; pl->V = V; pl->W = W; pl->M = M;
   pl->total_T = B ? t_off[B] : 0;  // offsets are absolute rows / entries of the caller's arrays
   pl->total_L = B ? l_off[B] : 0;
+  if (B > 0) {
+    pl->h_t_off.assign(t_off, t_off + B + 1);
+    pl->h_l_off.assign(l_off, l_off + B + 1);
+    if (pl->total_L > 0) pl->h_labels.assign(labels, labels + pl->total_L);
+  }
   cudaDeviceProp prop;
   cudaError_t ce = cudaGetDeviceProperties(&prop, device);
   if (ce != cudaSuccess) { delete pl; return cuda_fail(ce, "cudaGetDeviceProperties"); }
@@ -348,25 +368,89 @@ int kab_plan_run_host(kab_plan *pl, const float *h_log_probs, int32_t *h_best_pa
   if (!h_log_probs || !h_best_path || !h_best_labels || !h_best_scores || !h_status) return KAB_E_BAD_ARG;
   KAB_CUDA(cudaSetDevice(pl->device));
   const size_t n = (size_t)pl->total_T, B = (size_t)pl->B;
+  const int64_t V = pl->V;
   if (!pl->stream) {
     KAB_CUDA(cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking));
-    KAB_CUDA(cudaMalloc((void **)&pl->d_lp, n * pl->V * 4));
+    KAB_CUDA(cudaStreamCreateWithFlags(&pl->s_in, cudaStreamNonBlocking));
+    KAB_CUDA(cudaStreamCreateWithFlags(&pl->s_out, cudaStreamNonBlocking));
+    KAB_CUDA(cudaMalloc((void **)&pl->d_lp, n * V * 4));
     KAB_CUDA(cudaMalloc((void **)&pl->d_path, n * 4));
     KAB_CUDA(cudaMalloc((void **)&pl->d_lab, n * 4));
     KAB_CUDA(cudaMalloc((void **)&pl->d_sc, n * 4));
     KAB_CUDA(cudaMalloc((void **)&pl->d_fs, B * 4));
     KAB_CUDA(cudaMalloc((void **)&pl->d_st, B * 4));
+    // ---- cut the batch into segments of >= 32 MB of log-probs, at lattice boundaries whose
+    // first row is 16-byte aligned (bulk copies), at most 12 segments
+    const int64_t bytes_total = (int64_t)n * V * 4;
+    int want = (int)std::min<int64_t>(12, bytes_total / (32ll << 20));
+    if (want >= 2 && pl->h_t_off[0] == 0) {
+      std::vector<int64_t> cuts{0};
+      for (int k = 1; k < want; ++k) {
+        const int64_t target = (int64_t)n * k / want;
+        int64_t b = std::lower_bound(pl->h_t_off.begin(), pl->h_t_off.end(), target) - pl->h_t_off.begin();
+        while (b < (int64_t)B && (pl->h_t_off[b] * V) % 4 != 0) ++b;
+        if (b > cuts.back() && b < (int64_t)B) cuts.push_back(b);
+      }
+      if (cuts.size() >= 2) {
+        cuts.push_back((int64_t)B);
+        for (size_t k = 0; k + 1 < cuts.size(); ++k) {
+          const int64_t b0 = cuts[k], b1 = cuts[k + 1];
+          std::vector<int64_t> to(pl->h_t_off.begin() + b0, pl->h_t_off.begin() + b1 + 1);
+          std::vector<int64_t> lo(pl->h_l_off.begin() + b0, pl->h_l_off.begin() + b1 + 1);
+          const int64_t t0 = to[0], l0 = lo[0];
+          for (auto &x : to) x -= t0;
+          for (auto &x : lo) x -= l0;
+          kab_plan *c = nullptr;
+          const int32_t *lab = pl->h_labels.empty() ? nullptr : pl->h_labels.data() + l0;
+          int rc = kab_plan_create(&c, pl->device, b1 - b0, to.data(), lab, lo.data(), pl->V, pl->W, pl->M);
+          if (rc != KAB_OK) return rc;
+          c->is_child = true;
+          pl->segs.push_back(c);
+          pl->seg_b0.push_back(b0);
+          cudaEvent_t e1, e2;
+          KAB_CUDA(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+          KAB_CUDA(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+          pl->ev_in.push_back(e1);
+          pl->ev_cmp.push_back(e2);
+        }
+      }
+    }
   }
-  cudaStream_t s = pl->stream;
-  KAB_CUDA(cudaMemcpyAsync(pl->d_lp, h_log_probs, n * pl->V * 4, cudaMemcpyHostToDevice, s));
-  int rc = kab_plan_run_device(pl, pl->d_lp, pl->d_path, pl->d_lab, pl->d_sc, pl->d_fs, pl->d_st, s);
-  if (rc != KAB_OK) return rc;
-  KAB_CUDA(cudaMemcpyAsync(h_best_path, pl->d_path, n * 4, cudaMemcpyDeviceToHost, s));
-  KAB_CUDA(cudaMemcpyAsync(h_best_labels, pl->d_lab, n * 4, cudaMemcpyDeviceToHost, s));
-  KAB_CUDA(cudaMemcpyAsync(h_best_scores, pl->d_sc, n * 4, cudaMemcpyDeviceToHost, s));
-  if (h_final_score) KAB_CUDA(cudaMemcpyAsync(h_final_score, pl->d_fs, B * 4, cudaMemcpyDeviceToHost, s));
-  KAB_CUDA(cudaMemcpyAsync(h_status, pl->d_st, B * 4, cudaMemcpyDeviceToHost, s));
-  KAB_CUDA(cudaStreamSynchronize(s));
+  if (pl->segs.empty()) {  // small batch: one copy in, one run, one copy out
+    cudaStream_t s = pl->stream;
+    KAB_CUDA(cudaMemcpyAsync(pl->d_lp, h_log_probs, n * V * 4, cudaMemcpyHostToDevice, s));
+    int rc = kab_plan_run_device(pl, pl->d_lp, pl->d_path, pl->d_lab, pl->d_sc, pl->d_fs, pl->d_st, s);
+    if (rc != KAB_OK) return rc;
+    KAB_CUDA(cudaMemcpyAsync(h_best_path, pl->d_path, n * 4, cudaMemcpyDeviceToHost, s));
+    KAB_CUDA(cudaMemcpyAsync(h_best_labels, pl->d_lab, n * 4, cudaMemcpyDeviceToHost, s));
+    KAB_CUDA(cudaMemcpyAsync(h_best_scores, pl->d_sc, n * 4, cudaMemcpyDeviceToHost, s));
+    if (h_final_score) KAB_CUDA(cudaMemcpyAsync(h_final_score, pl->d_fs, B * 4, cudaMemcpyDeviceToHost, s));
+    KAB_CUDA(cudaMemcpyAsync(h_status, pl->d_st, B * 4, cudaMemcpyDeviceToHost, s));
+    KAB_CUDA(cudaStreamSynchronize(s));
+    return KAB_OK;
+  }
+  // ---- pipelined: three streams (copy in / kernels / copy out), one event pair per segment
+  for (size_t k = 0; k < pl->segs.size(); ++k) {
+    kab_plan *c = pl->segs[k];
+    const size_t b0 = (size_t)pl->seg_b0[k], t0 = (size_t)pl->h_t_off[b0];
+    const size_t nk = (size_t)c->total_T, bk = (size_t)c->B;
+    KAB_CUDA(cudaMemcpyAsync(pl->d_lp + t0 * V, h_log_probs + t0 * V, nk * V * 4, cudaMemcpyHostToDevice, pl->s_in));
+    KAB_CUDA(cudaEventRecord(pl->ev_in[k], pl->s_in));
+    KAB_CUDA(cudaStreamWaitEvent(pl->stream, pl->ev_in[k], 0));
+    int rc = kab_plan_run_device(c, pl->d_lp + t0 * V, pl->d_path + t0, pl->d_lab + t0, pl->d_sc + t0,
+                                 pl->d_fs + b0, pl->d_st + b0, pl->stream);
+    if (rc != KAB_OK) return rc;
+    KAB_CUDA(cudaEventRecord(pl->ev_cmp[k], pl->stream));
+    KAB_CUDA(cudaStreamWaitEvent(pl->s_out, pl->ev_cmp[k], 0));
+    KAB_CUDA(cudaMemcpyAsync(h_best_path + t0, pl->d_path + t0, nk * 4, cudaMemcpyDeviceToHost, pl->s_out));
+    KAB_CUDA(cudaMemcpyAsync(h_best_labels + t0, pl->d_lab + t0, nk * 4, cudaMemcpyDeviceToHost, pl->s_out));
+    KAB_CUDA(cudaMemcpyAsync(h_best_scores + t0, pl->d_sc + t0, nk * 4, cudaMemcpyDeviceToHost, pl->s_out));
+    if (h_final_score)
+      KAB_CUDA(cudaMemcpyAsync(h_final_score + b0, pl->d_fs + b0, bk * 4, cudaMemcpyDeviceToHost, pl->s_out));
+    KAB_CUDA(cudaMemcpyAsync(h_status + b0, pl->d_st + b0, bk * 4, cudaMemcpyDeviceToHost, pl->s_out));
+  }
+  KAB_CUDA(cudaStreamSynchronize(pl->s_out));
+  KAB_CUDA(cudaStreamSynchronize(pl->stream));
   return KAB_OK;
 }
 

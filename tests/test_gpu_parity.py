@@ -139,3 +139,31 @@ def test_full_size_properties(kab):
     rp, _, _, rf = ctc_oracle.ctc_best_path(lp, labels, return_final_score=True)
     np.testing.assert_array_equal(path, rp)
     assert np.float32(final).tobytes() == np.float32(rf).tobytes()
+
+
+def test_pipelined_host_path(kab):
+    """A batch large enough (>= 64 MB of log-probs) for kab_plan_run_host to cut it into
+    segments and overlap H2D / kernels / D2H; results must not depend on the segmentation."""
+    from kokoro_align_b200 import synth
+    T, L = synth.segment_lengths(2200, seed=2300)
+    lp, t_off, labels, l_off = synth.make_batch_fast(T, L, seed=2301)
+    assert lp.nbytes >= 96 << 20
+    labels = labels.copy()
+    labels[l_off[1500] + 2] = 39            # one bad-label lattice in a later segment
+    _compare_batch(kab, lp, t_off, labels, l_off)
+
+
+def test_align_sharded_single_rank(kab):
+    from kokoro_align_b200 import parallel, synth
+    from oracle import ctc_oracle
+    lps, labs = [], []
+    for k, t in enumerate((90, 400, 3000, 700)):
+        a, b = synth.make_lattice(t, int(round(0.14 * t)), 39, seed=2400 + k)
+        lps.append(a)
+        labs.append(b)
+    res = parallel.align_sharded(lps, labs)
+    for (path, _, _, final, status), lp, lab in zip(res, lps, labs):
+        rp, _, _, rf = ctc_oracle.ctc_best_path(lp, lab, return_final_score=True)
+        assert status == 0
+        np.testing.assert_array_equal(path, rp)
+        assert np.float32(final).tobytes() == np.float32(rf).tobytes()

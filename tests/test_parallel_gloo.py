@@ -1,0 +1,95 @@
+"""N > 1 host path on CPU: world_size-2 gloo.  The CUDA aligner is replaced by the CPU oracle
+(tests only) so that partitioning, sharded execution, the result gather and the timing
+reductions are exercised without a GPU."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _oracle_align(lp, t_off, labels, l_off, V, beam_size, max_move, device):
+    from oracle import ctc_oracle
+    return ctc_oracle.ctc_best_path_batch(lp, t_off, labels, l_off, beam_size, max_move, n_threads=1)
+
+
+def _make(n=9):
+    from kokoro_align_b200 import synth
+    T = np.array([40, 300, 120, 75, 900, 33, 210, 64, 500][:n])
+    L = np.maximum(1, np.round(0.14 * T)).astype(np.int64)
+    lps, labs = [], []
+    for k, (t, l) in enumerate(zip(T, L)):
+        a, b = synth.make_lattice(int(t), int(l), 39, seed=900 + k)
+        lps.append(a)
+        labs.append(b)
+    return lps, labs
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    from kokoro_align_b200 import parallel
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lps, labs = _make()
+    res = parallel.align_sharded(lps, labs, align_fn=_oracle_align)
+    tmax = parallel.max_over_ranks(1.0 + rank)
+    tsum = parallel.sum_over_ranks(10.0 * (rank + 1))
+    mine = parallel.shard_batch([len(x) for x in lps], [len(x) for x in labs], rank, world)
+    if rank == 0:
+        q.put(([(r[0].tolist(), r[3], r[4]) for r in res], tmax, tsum, mine.tolist()))
+    else:
+        assert res is None
+        q.put((None, tmax, tsum, mine.tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_alignment_world2():
+    from oracle import ctc_oracle
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    outs = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    res = next(o[0] for o in outs if o[0] is not None)
+    lps, labs = _make()
+    assert len(res) == len(lps)
+    for (path, final, status), lp, lab in zip(res, lps, labs):
+        rp, _, _, rf = ctc_oracle.ctc_best_path(lp, lab, return_final_score=True)
+        assert status == 0 and path == rp.tolist() and np.float32(final) == np.float32(rf)
+    assert all(o[1] == 2.0 for o in outs) and all(o[2] == 30.0 for o in outs)
+    shards = sorted(i for o in outs for i in o[3])
+    assert shards == list(range(len(lps)))          # every lattice exactly once
+
+
+def test_lpt_partition_properties():
+    from kokoro_align_b200 import parallel
+    rng = np.random.default_rng(0)
+    costs = rng.integers(1, 1000, 200)
+    for n in (1, 2, 4, 8):
+        parts = parallel.lpt_partition(costs, n)
+        allidx = np.sort(np.concatenate(parts))
+        assert allidx.tolist() == list(range(200))
+        loads = np.array([costs[p].sum() for p in parts])
+        assert loads.max() - costs.sum() / n <= costs.max()
+    assert parallel.lpt_partition([], 3)[0].size == 0
+
+
+def test_cells_eval_matches_oracle():
+    from kokoro_align_b200 import parallel
+    from oracle import ctc_oracle
+    for T, L, W in ((81135, 11359, 1000), (861, 121, 1000), (100, 300, 20), (1500, 450, 1000), (1, 0, 5)):
+        assert parallel.cells_eval(T, L, W) == ctc_oracle.cells_eval(T, L, W)
