@@ -274,7 +274,7 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
 
     // ---- launch geometry
     if (!pl->lists[Q_WARP].empty()) {
-      const size_t smem = 128 + (size_t)KAB_WARPS_PER_CTA * KAB_WARP_STAGES * pl->stage_bytes;
+      const size_t smem = 128 + (size_t)KAB_WARPS_PER_CTA * (KAB_WARP_STAGES * pl->stage_bytes + 256);  // + label tables
       const void *fn = V == 39 ? (const void *)kab_warp_kernel<39> : (const void *)kab_warp_kernel<0>;
       if ((e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) { rc = cuda_fail(e, "cudaFuncSetAttribute(warp)"); break; }
       int occ = 0;

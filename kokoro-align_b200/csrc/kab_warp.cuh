@@ -77,7 +77,7 @@ __device__ __forceinline__ void kab_warp_frame(float (&s)[K], const float eb, co
 // VCT: compile-time vocabulary (39) or 0 = runtime p.V.
 template <int K, int VCT>
 __device__ void kab_warp_align(const KabLattice &lat, const KabParams &p, float *stage_base, uint64_t *bars,
-                               uint32_t &chunk_counter, const int lane) {
+                               uint16_t *labtab, const uint64_t policy, uint32_t &chunk_counter, const int lane) {
   using Cfg = KabWarpCfg<K>;
   constexpr int BPF = Cfg::BPF, FPW = Cfg::FPW;
   const int T = lat.T, S = 2 * lat.L + 1;
@@ -96,7 +96,9 @@ __device__ void kab_warp_align(const KabLattice &lat, const KabParams &p, float 
 #pragma unroll
   for (int q = 0; q < K / 2; ++q) {
     const int v = sbase + 2 * q + 1;
-    coff[q] = (v > 0 && v < S) ? 4u * col16[(v - 1) >> 1] : 0u;
+    const uint32_t col = (v > 0 && v < S) ? col16[(v - 1) >> 1] : 0u;
+    coff[q] = 4u * col;
+    if (v > 0 && v < S) labtab[(v - 1) >> 1] = (uint16_t)col;  // per-warp copy for the backtrack's output rows
   }
 
   float s[K];
@@ -113,7 +115,7 @@ __device__ void kab_warp_align(const KabLattice &lat, const KabParams &p, float 
     float *dst = stage_base + st * stage_words;
     if (lane0) {
       kab_mbar_expect_tx(&bars[st], d.bytes);
-      if (d.bytes) kab_bulk_g2s(dst, d.src, d.bytes, &bars[st]);
+      if (d.bytes) kab_bulk_g2s_hint(dst, d.src, d.bytes, &bars[st], policy);
     }
     if (lane < (int)d.tail_n)  // last (< 16 B) words of the whole log_probs buffer
       dst[d.tail_word + lane] = __ldg(reinterpret_cast<const float *>(d.src) + d.tail_word + lane);
@@ -206,21 +208,28 @@ __device__ void kab_warp_align(const KabLattice &lat, const KabParams &p, float 
   if (status != 0) return;
 
   // -- backtrack (== flush_determined_path, align.py:21-40).  Word-rows are fetched four at a
-  // time (coalesced 128-byte rows, L2-resident: this warp wrote them moments ago), the walk
-  // reads the owner lane's word by shuffle, and every 32 frames the lanes flush one coalesced
-  // row of each output array.
+  // time, one block ahead of the walk (coalesced 128-byte rows; usually L2 hits: the emission
+  // rows stream through L2 evict-first), the walk reads the owner lane's word by shuffle, and
+  // every 32 frames the lanes flush one coalesced row of each output array.  The score gather
+  // of a row is issued at its flush and stored at the next one, so its DRAM latency is hidden.
   constexpr int RB = 4;  // word-rows per block
   int32_t *out_path = p.best_path + lat.t_off;
   int32_t *out_lab = p.best_labels + lat.t_off;
   float *out_sc = p.best_scores + lat.t_off;
   const float *lp = p.lp + lat.t_off * (int64_t)V;
   const int n_rows = (T + FPW - 1) / FPW;
-  int myv = 0;
-  for (int rb = ((n_rows - 1) / RB) * RB; rb >= 0; rb -= RB) {
-    uint32_t wr[RB];
+  auto fetch = [&](int rb, uint32_t (&w)[RB]) {
 #pragma unroll
     for (int r = 0; r < RB; ++r)
-      wr[r] = (rb + r) < n_rows ? __ldcg(&bpw[(size_t)(rb + r) * 32 + lane]) : 0u;
+      w[r] = (rb >= 0 && (rb + r) < n_rows) ? __ldcg(&bpw[(size_t)(rb + r) * 32 + lane]) : 0u;
+  };
+  int myv = 0, pend_t = -1;
+  float pend_s = 0.0f;
+  uint32_t wr[RB], wn[RB];
+  const int rb_last = ((n_rows - 1) / RB) * RB;
+  fetch(rb_last, wr);
+  for (int rb = rb_last; rb >= 0; rb -= RB) {
+    fetch(rb - RB, wn);
 #pragma unroll
     for (int r = RB - 1; r >= 0; --r) {
 #pragma unroll
@@ -236,15 +245,21 @@ __device__ void kab_warp_align(const KabLattice &lat, const KabParams &p, float 
     }
     const int fb = rb * FPW;  // first frame of the block; lanes hold frames (fb & ~31) .. +31
     if ((fb & 31) == 0) {
+      if (pend_t >= 0) out_sc[pend_t] = pend_s;  // gather issued one flush ago
       const int t = fb + lane;
+      pend_t = -1;
       if (t < T) {
-        const int lab = (myv & 1) ? (int)col16[(myv - 1) >> 1] : 0;
+        const int lab = (myv & 1) ? (int)labtab[(myv - 1) >> 1] : 0;
         out_path[t] = myv;
-        out_lab[t] = lab;                              // align.py:106
-        out_sc[t] = __ldg(&lp[(int64_t)t * V + lab]);  // align.py:107
+        out_lab[t] = lab;                           // align.py:106
+        pend_s = __ldg(&lp[(int64_t)t * V + lab]);  // align.py:107
+        pend_t = t;
       }
     }
+#pragma unroll
+    for (int r = 0; r < RB; ++r) wr[r] = wn[r];
   }
+  if (pend_t >= 0) out_sc[pend_t] = pend_s;
 }
 
 template <int VCT>
@@ -255,6 +270,10 @@ __global__ void __launch_bounds__(KAB_WARPS_PER_CTA * 32)
   uint64_t *bars = reinterpret_cast<uint64_t *>(kab_smem) + warp * KAB_WARP_STAGES;
   float *stage_base = reinterpret_cast<float *>(kab_smem + 128 +
                                                 (size_t)warp * KAB_WARP_STAGES * p.stage_bytes);
+  uint16_t *labtab = reinterpret_cast<uint16_t *>(kab_smem + 128 +
+                                                  (size_t)KAB_WARPS_PER_CTA * KAB_WARP_STAGES * p.stage_bytes) +
+                     warp * 128;  // labels of the warp's current lattice (<= 124)
+  const uint64_t policy = kab_policy_evict_first();
   if (lane == 0) {
     for (int s = 0; s < KAB_WARP_STAGES; ++s) kab_mbar_init(&bars[s], 1);
     kab_fence_mbar_init();
@@ -268,10 +287,10 @@ __global__ void __launch_bounds__(KAB_WARPS_PER_CTA * 32)
     if (item >= (unsigned int)n_lat) break;
     const KabLattice lat = lats[item];
     switch (lat.k) {
-      case 2: kab_warp_align<2, VCT>(lat, p, stage_base, bars, chunk_counter, lane); break;
-      case 4: kab_warp_align<4, VCT>(lat, p, stage_base, bars, chunk_counter, lane); break;
-      case 6: kab_warp_align<6, VCT>(lat, p, stage_base, bars, chunk_counter, lane); break;
-      default: kab_warp_align<8, VCT>(lat, p, stage_base, bars, chunk_counter, lane); break;
+      case 2: kab_warp_align<2, VCT>(lat, p, stage_base, bars, labtab, policy, chunk_counter, lane); break;
+      case 4: kab_warp_align<4, VCT>(lat, p, stage_base, bars, labtab, policy, chunk_counter, lane); break;
+      case 6: kab_warp_align<6, VCT>(lat, p, stage_base, bars, labtab, policy, chunk_counter, lane); break;
+      default: kab_warp_align<8, VCT>(lat, p, stage_base, bars, labtab, policy, chunk_counter, lane); break;
     }
     __syncwarp();
   }
