@@ -37,7 +37,7 @@ extern "C" {
 /* return codes */
 #define KAB_OK 0
 #define KAB_E_CUDA (-1)        /* CUDA runtime error, or no device */
-#define KAB_E_BAD_ARG (-2)     /* NULL pointer, negative size, max_move outside 1..16, T_b < 1 */
+#define KAB_E_BAD_ARG (-2)     /* NULL pointer, negative size, max_move outside 1..255, T_b < 1 */
 #define KAB_E_NOMEM (-3)       /* host allocation failed */
 #define KAB_E_UNSUPPORTED (-4) /* shape outside what the kernels handle (documented per call) */
 
@@ -48,8 +48,8 @@ extern "C" {
 #define KAB_ST_NONFINITE 3 /* a log-prob of the lattice is not finite (rejected) */
 
 /* kernel classes a lattice can be routed to (kab_plan_info) */
-#define KAB_CLASS_WARP 0    /* one warp per lattice, full window, S <= 256, max_move 4 */
-#define KAB_CLASS_BAND 1    /* one CTA per lattice, ring of beam_size+12 states, max_move 4 */
+#define KAB_CLASS_WARP 0    /* one warp per lattice, full window, S <= 248, max_move 4 */
+#define KAB_CLASS_BAND 1    /* one CTA per lattice, ring of >= beam_size+12 states in registers, max_move 4 */
 #define KAB_CLASS_GENERIC 2 /* any beam_size / max_move / label values */
 
 typedef struct kab_plan kab_plan; /* opaque */

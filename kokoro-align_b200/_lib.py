@@ -62,13 +62,16 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    if needs_build():
-        try:
-            build()
-        except (OSError, subprocess.CalledProcessError) as e:
-            if not os.path.exists(SO_PATH):
-                raise KabError(f"libkokoro_align_b200.so is missing and could not be built: {e}") from e
-    L = ctypes.CDLL(SO_PATH)
+    so = os.environ.get("KAB_LIBRARY")  # development: an alternative build of the same C ABI
+    if not so:
+        so = SO_PATH
+        if needs_build():
+            try:
+                build()
+            except (OSError, subprocess.CalledProcessError) as e:
+                if not os.path.exists(SO_PATH):
+                    raise KabError(f"libkokoro_align_b200.so is missing and could not be built: {e}") from e
+    L = ctypes.CDLL(so)
     vp, i32, i64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64
     L.kab_version.restype = ctypes.c_int
     L.kab_error_string.restype = ctypes.c_char_p

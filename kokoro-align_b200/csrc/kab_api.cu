@@ -30,10 +30,10 @@ int cuda_fail(cudaError_t e, const char *what) {
     if (e_ != cudaSuccess) return cuda_fail(e_, #call);   \
   } while (0)
 
-// kernel classes: 0 warp, 1..4 band with NT = 128/256/512/1024, 5 generic
-constexpr int N_QUEUES = 6;
-constexpr int Q_WARP = 0, Q_BAND0 = 1, Q_GENERIC = 5;
-constexpr int kBandNT[4] = {128, 256, 512, 1024};
+// kernel classes (one work queue each)
+constexpr int N_QUEUES = 3;
+constexpr int Q_WARP = 0, Q_BAND = 1, Q_GENERIC = 2;
+constexpr int BAND_MAX_WARPS = 32;
 constexpr int GENERIC_NT = 256;
 constexpr int MAX_STAGE_V = 128;  // widest vocabulary the staged (warp / band) kernels take
 
@@ -59,6 +59,7 @@ struct kab_plan {
   int32_t V = 0, W = 0, M = 0;
   int sm_count = 0;
   int32_t stage_frames = 0, stage_bytes = 0;
+  int32_t band_nw = 0;  // warps per CTA of the band kernel (ring of 104 * band_nw states)
   kab_plan_info info{};
   std::vector<KabLattice> lists[N_QUEUES];
   bool any_bad_label = false;
@@ -91,17 +92,6 @@ struct kab_plan {
 };
 
 namespace {
-
-template <int NT>
-int band_setup(kab_plan *pl, int q) {
-  const size_t smem = kab_band_smem_fixed<NT>() + (size_t)KAB_BAND_STAGES * pl->stage_bytes;
-  KAB_CUDA(cudaFuncSetAttribute(kab_band_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int occ = 0;
-  KAB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kab_band_kernel<NT>, NT, smem));
-  pl->smem[q] = smem;
-  pl->grid[q] = (int)std::min<int64_t>((int64_t)pl->lists[q].size(), (int64_t)pl->sm_count * std::max(occ, 1));
-  return KAB_OK;
-}
 
 int plan_free(kab_plan *pl) {
   if (!pl) return KAB_OK;
@@ -179,7 +169,7 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
   std::vector<uint16_t> col16;
   std::vector<int32_t> status_init((size_t)B, 0);
   col16.reserve((size_t)(pl->total_L + 16 * B + 16));
-  int64_t bp_bytes = 0, scr_floats = 0;
+  int64_t bp_bytes = 0, scr_floats = 0, max_band_weff = 0;
   kab_plan_info &info = pl->info;
   info.n_lattices = B; info.device = device; info.total_frames = pl->total_T;
   for (int64_t b = 0; b < B; ++b) {
@@ -218,11 +208,9 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
       const int fpw = d.k <= 2 ? 8 : (d.k <= 4 ? 4 : 2);
       d.bp_off = bp_bytes;
       bp_bytes += align_up((T + fpw - 1) / fpw * 128, 256);
-    } else if (fast && W >= 1 && S <= 3 * T && weff + 12 <= 4096) {
-      int nt_idx = weff + 12 <= 512 ? 0 : (weff + 12 <= 1024 ? 1 : (weff + 12 <= 2048 ? 2 : 3));
-      q = Q_BAND0 + nt_idx;
-      d.bp_off = bp_bytes;
-      bp_bytes += align_up((T + 3) / 4 * kBandNT[nt_idx] * 4, 256);
+    } else if (fast && W >= 1 && S <= 3 * T && weff + 32 <= KAB_BAND_OW * BAND_MAX_WARPS) {
+      q = Q_BAND;  // backpointer offsets are assigned below, once the ring size is known
+      max_band_weff = std::max(max_band_weff, weff);
     } else {
       q = Q_GENERIC;
       d.bp_off = bp_bytes;
@@ -239,6 +227,14 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
     while ((1 << bbits) < M) ++bbits;
     const int64_t dcols = std::min<int64_t>(V, distinct + 1);
     info.algorithmic_bytes += 4 * dcols * T + (cells * bbits + 7) / 8 + (T * bbits + 7) / 8 + 12 * T;
+  }
+  if (!pl->lists[Q_BAND].empty()) {
+    pl->band_nw = (int32_t)((max_band_weff + 32 + KAB_BAND_OW - 1) / KAB_BAND_OW);
+    const KabBandGeom geo = kab_band_geom(pl->band_nw, pl->stage_bytes);
+    for (KabLattice &d : pl->lists[Q_BAND]) {
+      d.bp_off = bp_bytes;
+      bp_bytes += align_up((int64_t)d.T * geo.nbp, 256);
+    }
   }
   // longest-processing-time-first order inside every queue
   for (int q = 0; q < N_QUEUES; ++q)
@@ -283,10 +279,15 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
       const int64_t ctas = ((int64_t)pl->lists[Q_WARP].size() + KAB_WARPS_PER_CTA - 1) / KAB_WARPS_PER_CTA;
       pl->grid[Q_WARP] = (int)std::min<int64_t>(ctas, (int64_t)pl->sm_count * std::max(occ, 1));
     }
-    if (!pl->lists[Q_BAND0 + 0].empty() && (rc = band_setup<128>(pl, Q_BAND0 + 0))) break;
-    if (!pl->lists[Q_BAND0 + 1].empty() && (rc = band_setup<256>(pl, Q_BAND0 + 1))) break;
-    if (!pl->lists[Q_BAND0 + 2].empty() && (rc = band_setup<512>(pl, Q_BAND0 + 2))) break;
-    if (!pl->lists[Q_BAND0 + 3].empty() && (rc = band_setup<1024>(pl, Q_BAND0 + 3))) break;
+    if (!pl->lists[Q_BAND].empty()) {
+      const KabBandGeom geo = kab_band_geom(pl->band_nw, pl->stage_bytes);
+      const void *fn = pl->band_nw <= 16 ? (const void *)kab_band_kernel<512> : (const void *)kab_band_kernel<1024>;
+      if ((e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)geo.smem_bytes)) != cudaSuccess) { rc = cuda_fail(e, "cudaFuncSetAttribute(band)"); break; }
+      int occ = 0;
+      if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, pl->band_nw * 32, geo.smem_bytes)) != cudaSuccess) { rc = cuda_fail(e, "occupancy(band)"); break; }
+      pl->smem[Q_BAND] = geo.smem_bytes;
+      pl->grid[Q_BAND] = (int)std::min<int64_t>((int64_t)pl->lists[Q_BAND].size(), (int64_t)pl->sm_count * std::max(occ, 1));
+    }
     if (!pl->lists[Q_GENERIC].empty())
       pl->grid[Q_GENERIC] = (int)std::min<int64_t>((int64_t)pl->lists[Q_GENERIC].size(), (int64_t)pl->sm_count * 4);
   } while (0);
@@ -326,6 +327,7 @@ int kab_plan_run_device(kab_plan *pl, const float *d_log_probs, int32_t *d_best_
   p.V = pl->V; p.W = pl->W; p.M = pl->M;
   p.stage_frames = pl->stage_frames; p.stage_bytes = pl->stage_bytes;
   p.one = 1u;
+  p.band_nw = pl->band_nw;
 
   KAB_CUDA(cudaMemsetAsync(pl->d_queue, 0, N_QUEUES * sizeof(unsigned int), stream));
   if (pl->any_bad_label)
@@ -340,17 +342,30 @@ int kab_plan_run_device(kab_plan *pl, const float *d_log_probs, int32_t *d_best_
       kab_warp_kernel<0><<<pl->grid[Q_WARP], KAB_WARPS_PER_CTA * 32, pl->smem[Q_WARP], stream>>>(
           pl->d_lists[Q_WARP], (int)pl->lists[Q_WARP].size(), pw);
   }
-  for (int b = 0; b < 4; ++b) {
-    const int q = Q_BAND0 + b;
-    if (pl->lists[q].empty()) continue;
-    KabParams pb = p; pb.queue = pl->d_queue + q;
-    const int n = (int)pl->lists[q].size();
-    switch (b) {
-      case 0: kab_band_kernel<128><<<pl->grid[q], 128, pl->smem[q], stream>>>(pl->d_lists[q], n, pb); break;
-      case 1: kab_band_kernel<256><<<pl->grid[q], 256, pl->smem[q], stream>>>(pl->d_lists[q], n, pb); break;
-      case 2: kab_band_kernel<512><<<pl->grid[q], 512, pl->smem[q], stream>>>(pl->d_lists[q], n, pb); break;
-      default: kab_band_kernel<1024><<<pl->grid[q], 1024, pl->smem[q], stream>>>(pl->d_lists[q], n, pb); break;
+  if (!pl->lists[Q_BAND].empty()) {
+    KabParams pb = p; pb.queue = pl->d_queue + Q_BAND;
+#ifdef KAB_BAND_TIMING
+    static long long *dbg = nullptr;
+    if (!dbg) cudaMalloc((void **)&dbg, 32 * 8 * sizeof(long long));
+    cudaMemsetAsync(dbg, 0, 32 * 8 * sizeof(long long), stream);
+    pb.debug = dbg;
+#endif
+    if (pl->band_nw <= 16)
+      kab_band_kernel<512><<<pl->grid[Q_BAND], pl->band_nw * 32, pl->smem[Q_BAND], stream>>>(
+          pl->d_lists[Q_BAND], (int)pl->lists[Q_BAND].size(), pb);
+    else
+      kab_band_kernel<1024><<<pl->grid[Q_BAND], pl->band_nw * 32, pl->smem[Q_BAND], stream>>>(
+          pl->d_lists[Q_BAND], (int)pl->lists[Q_BAND].size(), pb);
+#ifdef KAB_BAND_TIMING
+    {
+      long long h[32 * 8];
+      cudaStreamSynchronize(stream);
+      cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
+      for (int w = 0; w < pl->band_nw; ++w)
+        fprintf(stderr, "warp %2d: fast %lld cyc / %lld groups, slow %lld / %lld, epi %lld, bar %lld, post %lld, total %lld\n", w,
+                h[w * 8 + 0], h[w * 8 + 1], h[w * 8 + 2], h[w * 8 + 3], h[w * 8 + 4], h[w * 8 + 5], h[w * 8 + 6], h[w * 8 + 7]);
     }
+#endif
   }
   if (!pl->lists[Q_GENERIC].empty()) {
     KabParams pg = p; pg.queue = pl->d_queue + Q_GENERIC;
