@@ -52,7 +52,7 @@ __host__ __device__ inline KabBandGeom kab_band_geom(int nw, int stage_bytes) {
   g.xchg_off = 128;                                   // after the mbarriers
   g.bp_off = g.xchg_off + 2 * (size_t)nw * KAB_BAND_GHOST * 16;
   g.path_off = g.bp_off + 2 * (size_t)g.fb * g.nbp;
-  g.stage_off = (g.path_off + (size_t)g.fb * 4 + 15) & ~(size_t)15;
+  g.stage_off = (g.path_off + 2 * (size_t)g.fb * 4 + 15) & ~(size_t)15;  // two path buffers
   g.smem_bytes = g.stage_off + (size_t)KAB_BAND_STAGES * stage_bytes;
   return g;
 }
@@ -403,33 +403,47 @@ __global__ void __launch_bounds__(MAXT, 1) kab_band_kernel(const KabLattice *__r
       int32_t *out_lab = p.best_labels + lat.t_off;
       float *out_sc = p.best_scores + lat.t_off;
       const float *lp = p.lp + lat.t_off * (int64_t)V;
-      int slot = v % R;  // ring slot of the walker's state, kept incrementally
-      for (int blk = n_blocks - 1; blk >= 0; --blk) {
-        const uint32_t gi = bb0 + (uint32_t)(n_blocks - 1 - blk), bs = gi & 1u;
+      // Warp 0 walks a block while the other warps write the previous block's outputs.
+      int slot = v % R;  // ring slot of the walker's state
+      auto flush_block = [&](int blk, int first_thread, int n_threads) {
         const int i0 = blk * FB, i1 = min(T, i0 + FB);
-        if (tid == 0) {
-          if (blk > 0) fetch(blk - 1);  // other buffer: its previous contents were consumed
-          kab_mbar_wait(&bbars[bs], (gi >> 1) & 1u);
-          const unsigned char *rowp = bpblk + (size_t)bs * BPB + (size_t)(i1 - 1 - i0) * NBP;
-          for (int i = i1 - 1; i >= i0; --i, rowp -= NBP) {
-            const unsigned char byte = rowp[slot >> 2];
-            pathbuf[i - i0] = v;
-            const int mv = kab_decode_move((byte >> (2 * (slot & 3))) & 3u, v);
-            v -= mv;
-            slot -= mv;
-            if (slot < 0) slot += R;
-          }
-        }
-        __syncthreads();
-        for (int i = i0 + tid; i < i1; i += NT) {
-          const int pv = pathbuf[i - i0];
+        const int *pbuf = pathbuf + (blk & 1) * FB;
+        for (int i = i0 + (tid - first_thread); i < i1; i += n_threads) {
+          const int pv = pbuf[i - i0];
           const int lab = (pv & 1) ? (int)col16[(pv - 1) >> 1] : 0;
           out_path[i] = pv;
           out_lab[i] = lab;                              // align.py:106
           out_sc[i] = __ldg(&lp[(int64_t)i * V + lab]);  // align.py:107
         }
+      };
+      for (int blk = n_blocks - 1; blk >= 0; --blk) {
+        const uint32_t gi = bb0 + (uint32_t)(n_blocks - 1 - blk), bs = gi & 1u;
+        const int i0 = blk * FB, i1 = min(T, i0 + FB);
+        if (warp == 0) {
+          if (lane == 0 && blk > 0) fetch(blk - 1);  // other buffer: its previous contents were consumed
+          kab_mbar_wait(&bbars[bs], (gi >> 1) & 1u);
+          const unsigned char *blkp = bpblk + (size_t)bs * BPB;
+          int *pbuf = pathbuf + (blk & 1) * FB;
+          if (lane == 0) {  // the walk itself is a dependent chain: one lane, shared-memory latency
+            const unsigned char *rowp = blkp + (size_t)(i1 - 1 - i0) * NBP;
+            for (int i = i1 - 1; i >= i0; --i, rowp -= NBP) {
+              const unsigned char byte = rowp[slot >> 2];
+              pbuf[i - i0] = v;
+              const int mv = kab_decode_move((byte >> (2 * (slot & 3))) & 3u, v);
+              v -= mv;
+              slot -= mv;
+              if (slot < 0) slot += R;
+            }
+          }
+          v = __shfl_sync(KAB_FULL_MASK, v, 0);
+          slot = __shfl_sync(KAB_FULL_MASK, slot, 0);
+          if (NW == 1 && blk + 1 < n_blocks) { __syncwarp(); flush_block(blk + 1, 0, 32); }
+        } else if (blk + 1 < n_blocks) {
+          flush_block(blk + 1, 32, NT - 32);
+        }
         __syncthreads();
       }
+      flush_block(0, 0, NT);
       bblocks = bb0 + n_blocks;
     }
     __syncthreads();
