@@ -397,7 +397,9 @@ int kab_plan_run_host(kab_plan *pl, const float *h_log_probs, int32_t *h_best_pa
     // ---- cut the batch into segments of >= 32 MB of log-probs, at lattice boundaries whose
     // first row is 16-byte aligned (bulk copies), at most 12 segments
     const int64_t bytes_total = (int64_t)n * V * 4;
-    int want = (int)std::min<int64_t>(12, bytes_total / (32ll << 20));
+    // (only worthwhile when every segment still holds enough lattices to fill the GPU: a few
+    // long chapters are better off in one launch, where they run side by side)
+    int want = (int)std::min<int64_t>(std::min<int64_t>(12, bytes_total / (32ll << 20)), (int64_t)B / 512);
     if (want >= 2 && pl->h_t_off[0] == 0) {
       std::vector<int64_t> cuts{0};
       for (int k = 1; k < want; ++k) {
