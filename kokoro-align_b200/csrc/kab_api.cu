@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -163,6 +164,10 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
 
   // emission staging geometry: ~4 KB stages, at most 16 frames each
   pl->stage_frames = V <= 64 ? 16 : 8;  // multiple of 8: frame groups never straddle stages
+  if (const char *sf = getenv("KAB_STAGE_FRAMES")) {  // development knob: 8 or 16
+    const int v = atoi(sf);
+    if (v == 8 || v == 16 || v == 32) pl->stage_frames = v;
+  }
   pl->stage_bytes = (int32_t)align_up((int64_t)pl->stage_frames * V * 4 + 24, 16);
 
   // ---- classify, build the padded column table (numpy-style wrap of negative labels)
@@ -277,6 +282,11 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
       if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, KAB_WARPS_PER_CTA * 32, smem)) != cudaSuccess) { rc = cuda_fail(e, "occupancy(warp)"); break; }
       pl->smem[Q_WARP] = smem;
       const int64_t ctas = ((int64_t)pl->lists[Q_WARP].size() + KAB_WARPS_PER_CTA - 1) / KAB_WARPS_PER_CTA;
+      occ = std::min(occ, KAB_WARP_MINBLOCKS);
+      if (const char *cs = getenv("KAB_WARP_CTAS_PER_SM")) {  // development knob
+        const int v = atoi(cs);
+        if (v >= 1) occ = std::min(occ, v);
+      }
       pl->grid[Q_WARP] = (int)std::min<int64_t>(ctas, (int64_t)pl->sm_count * std::max(occ, 1));
     }
     if (!pl->lists[Q_BAND].empty()) {

@@ -24,6 +24,10 @@
 
 #define KAB_WARP_STAGES 3
 #define KAB_WARPS_PER_CTA 4
+#ifndef KAB_WARP_MINBLOCKS
+#define KAB_WARP_MINBLOCKS 5  // resident CTAs per SM (20 warps): measured optimum for the mixed-length
+                              // config-2 batch; more resident warps only lengthen the longest lattices
+#endif
 
 template <int K>
 struct KabWarpCfg {
@@ -263,7 +267,7 @@ __device__ void kab_warp_align(const KabLattice &lat, const KabParams &p, float 
 }
 
 template <int VCT>
-__global__ void __launch_bounds__(KAB_WARPS_PER_CTA * 32)
+__global__ void __launch_bounds__(KAB_WARPS_PER_CTA * 32, KAB_WARP_MINBLOCKS)
     kab_warp_kernel(const KabLattice *__restrict__ lats, int n_lat, KabParams p) {
   extern __shared__ __align__(128) unsigned char kab_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
