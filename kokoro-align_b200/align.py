@@ -179,3 +179,84 @@ def best_path(input_file, voca_file, output_file):
     labels = read_transcript_labels(voca_file)
     path, labs, scores = ctc_best_path(log_probs, labels)
     np.savez(output_file, best_path=path, best_labels=labs, best_scores=scores)
+
+
+# --------------------------------------------------------------------------- the consumer
+# the step that reads best_path.npz (align.py:127-169).  Host-side text
+# work; it defines the output contract of the kernels (best_path // 2 at the segment
+# boundaries, per-segment sums of best_scores), so it lives beside them.
+
+_PUNCT = (',', '.', '!', '?')
+
+
+class TokenTable:
+    """label index -> token index table of a ``text|voca`` transcript (the behaviour of
+    transcript.py:13-57): a token owns the labels from the middle of the previous voiced token
+    to its own middle; punctuation-only tokens move the boundary without owning labels."""
+
+    def __init__(self, voca_file):
+        from .encoder import encode_text
+        self.texts, self.vocas, self.table = [], [], []
+        labels_seen, boundary = 0, 0
+        with open(voca_file) as f:
+            for n, line in enumerate(f):
+                text, voca = line.rstrip('\r\n').split('|')
+                self.texts.append(text)
+                self.vocas.append(voca)
+                k = len(encode_text(voca))
+                if k:
+                    labels_seen += k
+                    upto = labels_seen - k // 2
+                    self.table.extend([boundary] * (upto - len(self.table)))
+                    boundary = n + 1
+                elif voca in _PUNCT:
+                    boundary = n + 1
+
+    def __len__(self):
+        return len(self.table)
+
+    def get_token(self, start, end, remove_wordsep=True):
+        import re
+        lo = self.table[start] if start < len(self.table) else len(self.texts)
+        hi = self.table[end] if end < len(self.table) else len(self.texts)
+        text = ' '.join(t for t in self.texts[lo:hi] if t)
+        parts = [t for t in self.vocas[lo:hi] if t]
+        if remove_wordsep:
+            voca = ' '.join(parts)
+        else:
+            voca = ' _ '.join(parts)
+            voca = re.sub(r'_ ([.,!?])', r'\1', voca)
+            voca = re.sub(r'([.,!?]) _', r'\1', voca)
+        return text.strip(), voca.strip()
+
+
+def align(best_path_file, mfcc_file, voca_file, align_file, remove_wordsep):
+    """Drop-in for kokoro_align.align.align (align.py:127-169): one line per silence-split
+    segment, ``audio_end|text|voca|decoded|non_blanks|non_blanks_score|all_score``."""
+    import os
+    from .encoder import decode_text, merge_repeated
+    with np.load(best_path_file) as f:
+        label_idx = f['best_path'] // 2            # extended-state index -> label index
+        best_labels = f['best_labels']
+        best_scores = f['best_scores']
+    with np.load(mfcc_file) as f:
+        ends = f['indices']
+    table = TokenTable(voca_file)
+    n_frames = len(label_idx)
+    try:
+        with open(align_file, 'wt') as out:
+            for i in range(len(ends)):
+                a = ends[i - 1] if i > 0 else 0
+                b = ends[i]
+                t0 = min(label_idx[a], len(table))
+                t1 = min(label_idx[b] if b < n_frames else len(table), len(table))
+                labels = best_labels[a:b]
+                scores = best_scores[a:b]
+                voiced = labels != 0
+                decoded = merge_repeated(decode_text(labels))
+                text, voca = table.get_token(t0, t1, remove_wordsep=remove_wordsep)
+                out.write(f'{b}|{text}|{voca}|{decoded}|{np.sum(voiced).item()}|'
+                          f'{np.sum(scores[voiced]).item()}|{np.sum(scores).item()}\n')
+    except BaseException:
+        os.unlink(align_file)
+        raise

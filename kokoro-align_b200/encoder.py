@@ -17,3 +17,12 @@ def encode_text(text):
 
 def decode_text(encoded):
     return ' '.join(VOCAB[n] for n in encoded)
+
+
+def merge_repeated(text):
+    """Greedy CTC collapse of a decoded token string (the contract of encoder.py:26-31):
+    runs of an identical token sequence collapse to one copy, then blanks are dropped."""
+    import re
+    collapsed = re.sub(r'(.+)( \1)+', r'\1', text)
+    collapsed = collapsed.replace(' _', '').replace('_ ', '')
+    return '' if collapsed == '_' else collapsed

@@ -167,3 +167,23 @@ def test_align_sharded_single_rank(kab):
         assert status == 0
         np.testing.assert_array_equal(path, rp)
         assert np.float32(final).tobytes() == np.float32(rf).tobytes()
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6])
+def test_random_shapes_and_beams(kab, seed):
+    """Randomised (T, L, beam_size) batches: every ring size of the band kernel (1..32 warps),
+    class boundaries (S = 248/249, beam_size = 104k - 32 +- 1), tiny and degenerate lattices."""
+    from kokoro_align_b200 import synth
+    rng = np.random.default_rng(seed)
+    edge_beams = [1, 2, 5, 71, 72, 73, 175, 176, 177, 1000, 3295, 3296, 3297, 5000]
+    W = int(rng.choice(edge_beams)) if seed % 2 else int(rng.integers(1, 3400))
+    n = 40
+    T = rng.integers(1, 2500, n)
+    ratio = rng.choice([0.02, 0.14, 0.5, 1.0, 1.45], n)
+    L = np.minimum(np.maximum(0, np.round(ratio * T)).astype(np.int64), 3 * T)
+    L[:4] = [123, 124, 0, 1]                       # S = 247 / 249 straddle the warp-class limit
+    T[:4] = [900, 900, 1, 2]
+    lp, t_off, labels, l_off = synth.make_batch(T, L, seed=7000 + 100 * seed, planted=bool(seed % 2))
+    if seed % 3 == 0:                              # tie stress
+        lp = (np.round(lp * 2) / 2).astype(np.float32)
+    _compare_batch(kab, lp, t_off, labels, l_off, beam_size=W)
