@@ -133,30 +133,9 @@ __device__ __forceinline__ KabStageDesc kab_stage_desc(const KabParams &p, int64
 
 // ---------------------------------------------------------------- the two cell updates (M = 4)
 // Blank state (ext[v] == 0): moves 0, 1, 3 (move 2 = blank -> blank is forbidden, align.py:80-81).
-// Every candidate is one IEEE fp32 add (align.py:77); the scan is strict '>' in j order
-// (np.argmax returns the first maximum, align.py:83), so the smallest move wins ties.
-__device__ __forceinline__ float kab_cell_blank(float s0, float s1, float s3, float e, uint32_t &mv) {
-  const float a0 = __fadd_rn(s0, e), a1 = __fadd_rn(s1, e), a3 = __fadd_rn(s3, e);
-  const bool p1 = a1 > a0;
-  const float m = p1 ? a1 : a0;
-  const bool p3 = a3 > m;
-  mv = p3 ? 3u : (p1 ? 1u : 0u);
-  return p3 ? a3 : m;
-}
-// Label state: moves 0, 1, 2, 3.  Tournament form of the same ascending strict-'>' scan:
-// the winner of (0,1) vs the winner of (2,3); the upper pair wins only if strictly greater.
-__device__ __forceinline__ float kab_cell_label(float s0, float s1, float s2, float s3, float e,
-                                                uint32_t &mv) {
-  const float a0 = __fadd_rn(s0, e), a1 = __fadd_rn(s1, e), a2 = __fadd_rn(s2, e), a3 = __fadd_rn(s3, e);
-  const bool p01 = a1 > a0, p23 = a3 > a2;
-  const float m01 = p01 ? a1 : a0, m23 = p23 ? a3 : a2;
-  const bool ph = m23 > m01;
-  mv = ph ? (p23 ? 3u : 2u) : (p01 ? 1u : 0u);
-  return ph ? m23 : m01;
-}
-
-// ---------------------------------------------------------------- packed-backpointer cell updates
-// Same arithmetic and tie-break as kab_cell_blank / kab_cell_label, written in PTX:
+// Label state: moves 0, 1, 2, 3.  Every candidate is one IEEE fp32 add (align.py:77); the scan
+// is strict '>' in j order (np.argmax returns the first maximum, align.py:83), so the smallest
+// move wins ties.  Written in PTX:
 //   * the candidate sums come from packed fp32x2 adds (FADD2 on sm_100a: two IEEE-rn fp32 adds,
 //     second operand broadcast), so adjacent states (s[2m], s[2m+1]) share one instruction;
 //   * winners are taken with max.f32 (the candidates are never NaN and never -0, so max returns
