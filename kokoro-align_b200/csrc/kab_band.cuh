@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(MAXT, 1) kab_band_kernel(const KabLattice *__r
     load_cols(vb + R, nc1, nc3);
     const int half = W / 2;
 
-    bool bad = false;
+    float poison = 0.0f;  // NaN once a non-finite log-prob was staged (kab_poison)
     if (tid == 0) {
       kab_mbar_wait(&ebars[st], ph);
       if (F < 2 * G && n_chunks > 1) {  // F == G: chunk 1 opens at group 1, before the look-ahead wait
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(MAXT, 1) kab_band_kernel(const KabLattice *__r
     auto check_chunk = [&](int c) {  // finiteness of chunk c's words (all threads, strided)
       const float *w = stage_base + st * stage_words + skew;
       const int nw = min(F, T - c * F) * V;
-      for (int j = tid; j < nw; j += NT) bad |= !kab_finite(w[j]);
+      for (int j = tid; j < nw; j += NT) poison = kab_poison(poison, w[j]);
     };
     check_chunk(0);
     float eb = *reinterpret_cast<const float *>(rowc);
@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(MAXT, 1) kab_band_kernel(const KabLattice *__r
       if (lane == 0 && cand >= 0) atomicMax(&s_vmax, cand);
     }
     if (tid == 0) kab_bulk_wait0();  // all backpointer blocks are in global memory
-    const int any_bad = __syncthreads_or(bad ? 1 : 0);
+    const int any_bad = __syncthreads_or(poison != poison ? 1 : 0);
     int v = s_vmax;
     const int status = any_bad ? 3 : (v < 0 ? 1 : 0);
     if (owned && status == 0) {

@@ -47,6 +47,9 @@ struct KabParams {
 
 __device__ __forceinline__ float kab_neg_inf() { return __int_as_float(0xff800000); }
 __device__ __forceinline__ bool kab_finite(float x) { return fabsf(x) < __int_as_float(0x7f800000); }
+// Finiteness accumulator on the FMA pipe (the ALU pipe is the busy one): x * 0 is 0 for a finite x
+// and NaN for +-inf / NaN, so `acc` turns NaN, and stays NaN, once a non-finite value was seen.
+__device__ __forceinline__ float kab_poison(float acc, float x) { return fmaf(x, 0.0f, acc); }
 
 // ---------------------------------------------------------------- mbarrier + 1-D bulk copy (TMA)
 __device__ __forceinline__ uint32_t kab_smem_u32(const void *p) {

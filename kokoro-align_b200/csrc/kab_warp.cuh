@@ -127,7 +127,7 @@ __device__ void kab_warp_align(const KabLattice &lat, const KabParams &p, float 
   const int pre = min(n_chunks, KAB_WARP_STAGES - 1);
   for (int c = 0; c < pre; ++c) issue(c);
 
-  bool bad = false;
+  float poison = 0.0f;  // NaN once a non-finite log-prob was staged (kab_poison)
   uint32_t *bprow = bpw + lane;  // this lane's slot in the current word-row
   for (int c = 0; c < n_chunks; ++c) {
     // the stage consumed in iteration c-1 is free again: refill it with chunk c + STAGES - 1
@@ -146,10 +146,10 @@ __device__ void kab_warp_align(const KabLattice &lat, const KabParams &p, float 
       const float4 *s4 = reinterpret_cast<const float4 *>(stage);
       for (int j = v0 + lane; j < v1; j += 32) {
         const float4 x = s4[j];
-        bad |= !(kab_finite(x.x) && kab_finite(x.y) && kab_finite(x.z) && kab_finite(x.w));
+        poison = kab_poison(kab_poison(kab_poison(kab_poison(poison, x.x), x.y), x.z), x.w);
       }
-      if (lane < 4 * v0 - w0 && w0 + lane < w1) bad |= !kab_finite(stage[w0 + lane]);
-      if (4 * v1 >= w0 && lane < w1 - 4 * v1) bad |= !kab_finite(stage[4 * v1 + lane]);
+      if (lane < 4 * v0 - w0 && w0 + lane < w1) poison = kab_poison(poison, stage[w0 + lane]);
+      if (4 * v1 >= w0 && lane < w1 - 4 * v1) poison = kab_poison(poison, stage[4 * v1 + lane]);
     }
     const char *rowb = reinterpret_cast<const char *>(stage + w0);
     const int n_groups = nf / FPW;
@@ -194,7 +194,7 @@ __device__ void kab_warp_align(const KabLattice &lat, const KabParams &p, float 
     if (v >= 0 && v < S && s[k] > kab_neg_inf()) cand = v;
   }
   int v = __reduce_max_sync(KAB_FULL_MASK, cand);
-  const bool any_bad = __any_sync(KAB_FULL_MASK, bad);
+  const bool any_bad = __any_sync(KAB_FULL_MASK, poison != poison);
   const int status = any_bad ? 3 : (v < 0 ? 1 : 0);
   {
     float fs = __int_as_float(0x7fc00000);
