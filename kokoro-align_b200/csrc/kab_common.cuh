@@ -169,6 +169,20 @@ __device__ __forceinline__ int kab_decode_move(uint32_t code, int v) {
 __device__ __forceinline__ float kab_blank_sel(float a0, float a1, float a3, uint32_t &w, const uint32_t bit1,
                                                const uint32_t bit2, const uint32_t one) {
   float best;
+#ifndef KAB_SEL_V1
+  // The first maximum is the smallest move whose candidate EQUALS the 3-input maximum (FMNMX3):
+  // bit 0 = (move != 0), bit 1 = (move != 0 and move != 1), i.e. codes 0, 1, 3.
+  asm("{\n\t"
+      ".reg .pred p1, p3;\n\t"
+      "max.f32 %0, %2, %3, %4;\n\t"
+      "setp.neu.f32 p1, %2, %0;\n\t"
+      "setp.neu.and.f32 p3, %3, %0, p1;\n\t"
+      "@p1 mad.lo.u32 %1, %7, %5, %1;\n\t"
+      "@p3 mad.lo.u32 %1, %7, %6, %1;\n\t"
+      "}"
+      : "=f"(best), "+r"(w)
+      : "f"(a0), "f"(a1), "f"(a3), "r"(bit1), "r"(bit2), "r"(one));
+#else
   asm("{\n\t"
       ".reg .f32 m;\n\t"
       ".reg .pred p1, p3;\n\t"
@@ -181,6 +195,7 @@ __device__ __forceinline__ float kab_blank_sel(float a0, float a1, float a3, uin
       "}"
       : "=f"(best), "+r"(w)
       : "f"(a0), "f"(a1), "f"(a3), "r"(bit1), "r"(bit2), "r"(one));
+#endif
   return best;
 }
 // Label state: candidates a0..a3; tournament form of the ascending strict-'>' scan: the winner
@@ -188,6 +203,23 @@ __device__ __forceinline__ float kab_blank_sel(float a0, float a1, float a3, uin
 __device__ __forceinline__ float kab_label_sel(float a0, float a1, float a2, float a3, uint32_t &w,
                                                const uint32_t bit1, const uint32_t bit2, const uint32_t one) {
   float best;
+#ifndef KAB_SEL_V1
+  // m01 = max(a0, a1); best = max3(m01, a2, a3); the upper pair won iff best != m01 (strictly
+  // greater); the odd candidate of the winning pair won iff its even candidate != best.
+  asm("{\n\t"
+      ".reg .f32 m01, z;\n\t"
+      ".reg .pred ph, pl;\n\t"
+      "max.f32 m01, %2, %3;\n\t"
+      "max.f32 %0, m01, %4, %5;\n\t"
+      "setp.neu.f32 ph, m01, %0;\n\t"
+      "selp.f32 z, %4, %2, ph;\n\t"
+      "setp.neu.f32 pl, z, %0;\n\t"
+      "@pl mad.lo.u32 %1, %8, %6, %1;\n\t"
+      "@ph mad.lo.u32 %1, %8, %7, %1;\n\t"
+      "}"
+      : "=f"(best), "+r"(w)
+      : "f"(a0), "f"(a1), "f"(a2), "f"(a3), "r"(bit1), "r"(bit2), "r"(one));
+#else
   asm("{\n\t"
       ".reg .f32 m01, m23, z;\n\t"
       ".reg .pred ph, pl;\n\t"
@@ -202,5 +234,6 @@ __device__ __forceinline__ float kab_label_sel(float a0, float a1, float a2, flo
       "}"
       : "=f"(best), "+r"(w)
       : "f"(a0), "f"(a1), "f"(a2), "f"(a3), "r"(bit1), "r"(bit2), "r"(one));
+#endif
   return best;
 }
