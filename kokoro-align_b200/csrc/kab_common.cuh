@@ -161,10 +161,16 @@ __device__ __forceinline__ void kab_add2(float lo, float hi, float e, float &olo
 // ptxas cannot fold): IMAD runs on the FMA pipe, the compares/max/selects on the ALU pipe, and
 // both pipes issue at half rate on sm_100 -- this keeps them balanced.  The bits touched by one
 // frame are disjoint, so the adds never carry.
-// Blank-state code: bit 0 = (move 1 beat move 0), bit 1 = (move 3 beat both); decode with
-// kab_decode_move: code >= 2 -> move 3, else move = code.  Label-state code == move.
+// Backpointer codes: a label state stores its move (0..3); a blank state stores 0, 1 or 3 (bit 0 =
+// move != 0, bit 1 = move 3), so the 2-bit code is the move for both.  (The KAB_SEL_V1 selects set
+// blank bit 1 alone for move 3: there code >= 2 decodes to 3.)
 __device__ __forceinline__ int kab_decode_move(uint32_t code, int v) {
+#ifndef KAB_SEL_V1
+  (void)v;
+  return (int)code;
+#else
   return ((v & 1) == 0 && code >= 2u) ? 3 : (int)code;
+#endif
 }
 __device__ __forceinline__ float kab_blank_sel(float a0, float a1, float a3, uint32_t &w, const uint32_t bit1,
                                                const uint32_t bit2, const uint32_t one) {

@@ -227,27 +227,33 @@ __device__ void kab_warp_align(const KabLattice &lat, const KabParams &p, float 
     for (int r = 0; r < RB; ++r)
       w[r] = (rb >= 0 && (rb + r) < n_rows) ? __ldcg(&bpw[(size_t)(rb + r) * 32 + lane]) : 0u;
   };
+  // The walk keeps the state as (own1, k2) = (owner lane, 2 * index inside the lane) next to v,
+  // so a frame costs one shuffle, one shift/mask and a few adds: the 2-bit code IS the move
+  // (kab_decode_move).  Frames >= T of the last block have all-zero codes (moves 0), so the
+  // block bodies need no bounds checks.
   int myv = 0, pend_t = -1;
   float pend_s = 0.0f;
+  int own1 = v / K + 1, k2 = 2 * (v - (v / K) * K);
   uint32_t wr[RB], wn[RB];
   const int rb_last = ((n_rows - 1) / RB) * RB;
   fetch(rb_last, wr);
   for (int rb = rb_last; rb >= 0; rb -= RB) {
     fetch(rb - RB, wn);
+    const int fb = rb * FPW;            // first frame of the block (a multiple of RB * FPW, which divides 32)
+    const int lb = lane - (fb & 31);    // lane records frame fb + off iff lb == off
 #pragma unroll
     for (int r = RB - 1; r >= 0; --r) {
 #pragma unroll
       for (int f = FPW - 1; f >= 0; --f) {
-        const int fi = (rb + r) * FPW + f;  // frame index (warp-uniform)
-        if (fi < T) {
-          const int owner = v / K, k = v - owner * K;
-          const uint32_t w = __shfl_sync(KAB_FULL_MASK, wr[r], owner + 1);
-          if (lane == (fi & 31)) myv = v;
-          v -= kab_decode_move((w >> (f * BPF + 2 * k)) & 3u, v);
-        }
+        const uint32_t w = __shfl_sync(KAB_FULL_MASK, wr[r], own1);
+        if (lb == r * FPW + f) myv = v;
+        const int mv = (int)((w >> (f * BPF + k2)) & 3u);
+        v -= mv;
+        k2 -= 2 * mv;
+        if (k2 < 0) { k2 += 2 * K; --own1; }
+        if (K == 2 && k2 < 0) { k2 += 2 * K; --own1; }  // a move of 3 can cross two 2-state lanes
       }
     }
-    const int fb = rb * FPW;  // first frame of the block; lanes hold frames (fb & ~31) .. +31
     if ((fb & 31) == 0) {
       if (pend_t >= 0) out_sc[pend_t] = pend_s;  // gather issued one flush ago
       const int t = fb + lane;
