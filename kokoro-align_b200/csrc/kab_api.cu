@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "kab_band.cuh"
+#include "kab_bandp.cuh"
 #include "kab_common.cuh"
 #include "kab_generic.cuh"
 #include "kab_warp.cuh"
@@ -61,6 +62,7 @@ struct kab_plan {
   int sm_count = 0;
   int32_t stage_frames = 0, stage_bytes = 0;
   int32_t band_nw = 0;  // warps per CTA of the band kernel (ring of 104 * band_nw states)
+  int32_t band_nc = 0;  // > 0: the pipelined cluster kernel (kab_bandp.cuh) with clusters of band_nc CTAs
   kab_plan_info info{};
   std::vector<KabLattice> lists[N_QUEUES];
   bool any_bad_label = false;
@@ -235,10 +237,25 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
   }
   if (!pl->lists[Q_BAND].empty()) {
     pl->band_nw = (int32_t)((max_band_weff + 32 + KAB_BAND_OW - 1) / KAB_BAND_OW);
-    const KabBandGeom geo = kab_band_geom(pl->band_nw, pl->stage_bytes);
-    for (KabLattice &d : pl->lists[Q_BAND]) {
-      d.bp_off = bp_bytes;
-      bp_bytes += align_up((int64_t)d.T * geo.nbp, 256);
+    // KAB_BAND_CLUSTER=N (N >= 1) selects the pipelined cluster kernel (kab_bandp.cuh: rings of 4 * NC
+    // warps over a cluster of NC <= 8 CTAs, NC = max(N, what the band needs)).  It is bit-exact
+    // and tested, but on B200 it only matches the single-CTA kernel, so
+    // the single-CTA kernel stays the default.
+    const int nc = (pl->band_nw + KAB_BP_CW - 1) / KAB_BP_CW;
+    const char *cl = getenv("KAB_BAND_CLUSTER");
+    const int want_nc = cl ? atoi(cl) : 0;
+    if (nc <= 8 && want_nc >= 1) {
+      pl->band_nc = std::min(8, std::max(nc, want_nc));
+      for (KabLattice &d : pl->lists[Q_BAND]) {
+        d.bp_off = bp_bytes;
+        bp_bytes += (int64_t)((d.T + 7) / 8) * 256 * KAB_BP_CW * pl->band_nc;  // [warp][group][32 lanes][8 B]
+      }
+    } else {
+      const KabBandGeom geo = kab_band_geom(pl->band_nw, pl->stage_bytes);
+      for (KabLattice &d : pl->lists[Q_BAND]) {
+        d.bp_off = bp_bytes;
+        bp_bytes += align_up((int64_t)d.T * geo.nbp, 256);
+      }
     }
   }
   // longest-processing-time-first order inside every queue
@@ -289,7 +306,23 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
       }
       pl->grid[Q_WARP] = (int)std::min<int64_t>(ctas, (int64_t)pl->sm_count * std::max(occ, 1));
     }
-    if (!pl->lists[Q_BAND].empty()) {
+    if (!pl->lists[Q_BAND].empty() && pl->band_nc > 0) {
+      const KabBandpGeom geo = kab_bandp_geom(pl->stage_bytes);
+      if ((e = cudaFuncSetAttribute(kab_bandp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)geo.smem_bytes)) != cudaSuccess) { rc = cuda_fail(e, "cudaFuncSetAttribute(bandp)"); break; }
+      pl->smem[Q_BAND] = geo.smem_bytes;
+      cudaLaunchConfig_t cfg{};
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = (unsigned)pl->band_nc; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.gridDim = dim3((unsigned)(pl->band_nc * pl->sm_count), 1, 1);
+      cfg.blockDim = dim3(KAB_BP_THREADS, 1, 1);
+      cfg.dynamicSmemBytes = geo.smem_bytes;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      int ncl = 0;
+      if ((e = cudaOccupancyMaxActiveClusters(&ncl, kab_bandp_kernel, &cfg)) != cudaSuccess) { rc = cuda_fail(e, "cudaOccupancyMaxActiveClusters(bandp)"); break; }
+      ncl = (int)std::min<int64_t>(std::max(ncl, 1), (int64_t)pl->lists[Q_BAND].size());
+      pl->grid[Q_BAND] = ncl * pl->band_nc;
+    } else if (!pl->lists[Q_BAND].empty()) {
       const KabBandGeom geo = kab_band_geom(pl->band_nw, pl->stage_bytes);
       const void *fn = pl->band_nw <= 16 ? (const void *)kab_band_kernel<512> : (const void *)kab_band_kernel<1024>;
       if ((e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)geo.smem_bytes)) != cudaSuccess) { rc = cuda_fail(e, "cudaFuncSetAttribute(band)"); break; }
@@ -360,7 +393,41 @@ int kab_plan_run_device(kab_plan *pl, const float *d_log_probs, int32_t *d_best_
     cudaMemsetAsync(dbg, 0, 32 * 8 * sizeof(long long), stream);
     pb.debug = dbg;
 #endif
-    if (pl->band_nw <= 16)
+    if (pl->band_nc > 0) {
+#ifdef KAB_BANDP_TIMING
+      static long long *pdbg = nullptr;
+      if (!pdbg) cudaMalloc((void **)&pdbg, (32 * 16 + 8) * sizeof(long long));
+      cudaMemsetAsync(pdbg, 0, (32 * 16 + 8) * sizeof(long long), stream);
+      pb.debug = pdbg;
+      struct BandpDbgPrint {
+        long long *d; cudaStream_t s; int nw;
+        ~BandpDbgPrint() {
+          long long h[32 * 16 + 8];
+          cudaStreamSynchronize(s);
+          cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+          for (int w = 0; w < nw; ++w) {
+            const long long *x = h + w * 16;
+            const double n = (double)(x[7] ? x[7] : 1);
+            fprintf(stderr, "warp %2d: per group: ghost %5.0f (guard %4.0f) emis %4.0f comp %5.0f pub %4.0f rel %4.0f bp %4.0f | total %lld cyc, %lld groups, need %lld, safe %lld, wait/need %.0f, first-try %lld, comp safe %.0f slow %.0f\n",
+                    w, x[0] / n, x[8] / n, x[1] / n, x[2] / n, x[3] / n, x[4] / n, x[5] / n, x[6], x[7], x[9], x[10], x[9] ? (double)x[11] / x[9] : 0.0, x[12],
+                    x[10] ? (double)(x[2] - x[13]) / x[10] : 0.0, x[7] - x[10] ? (double)x[13] / (x[7] - x[10]) : 0.0);
+          }
+          fprintf(stderr, "backtrack %lld cyc\n", h[32 * 16]);
+        }
+      } pdbg_print{pdbg, stream, KAB_BP_CW * pl->band_nc};
+#endif
+      cudaLaunchConfig_t cfg{};
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = (unsigned)pl->band_nc; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.gridDim = dim3((unsigned)pl->grid[Q_BAND], 1, 1);
+      cfg.blockDim = dim3(KAB_BP_THREADS, 1, 1);
+      cfg.dynamicSmemBytes = pl->smem[Q_BAND];
+      cfg.stream = stream;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      KAB_CUDA(cudaLaunchKernelEx(&cfg, kab_bandp_kernel, (const KabLattice *)pl->d_lists[Q_BAND],
+                                  (int)pl->lists[Q_BAND].size(), pb));
+    } else if (pl->band_nw <= 16)
       kab_band_kernel<512><<<pl->grid[Q_BAND], pl->band_nw * 32, pl->smem[Q_BAND], stream>>>(
           pl->d_lists[Q_BAND], (int)pl->lists[Q_BAND].size(), pb);
     else

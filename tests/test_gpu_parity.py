@@ -187,3 +187,17 @@ def test_random_shapes_and_beams(kab, seed):
     if seed % 3 == 0:                              # tie stress
         lp = (np.round(lp * 2) / 2).astype(np.float32)
     _compare_batch(kab, lp, t_off, labels, l_off, beam_size=W)
+
+
+@pytest.mark.parametrize("beam_size,cluster", [(1000, 1), (64, 1), (200, 2)])
+def test_cluster_band_kernel(kab, monkeypatch, beam_size, cluster):
+    """The opt-in pipelined cluster kernel (kab_bandp.cuh, KAB_BAND_CLUSTER) against the C oracle:
+    bit-exact like the default single-CTA band kernel."""
+    from kokoro_align_b200 import synth
+    monkeypatch.setenv("KAB_BAND_CLUSTER", str(cluster))
+    T = np.array([12000, 7001, 3000, 41, 5003])
+    L = np.round(0.14 * T).astype(np.int64)
+    L[4] = 1700  # S/T = 0.68: the walker changes warp regions often
+    lp, t_off, labels, l_off = synth.make_batch(T, L, seed=4300 + beam_size, planted=True)
+    info = _compare_batch(kab, lp, t_off, labels, l_off, beam_size=beam_size)
+    assert info.n_class[1] >= 4
