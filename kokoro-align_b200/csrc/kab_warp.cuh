@@ -110,37 +110,53 @@ __device__ void kab_warp_align(const KabLattice &lat, const KabParams &p, float 
   for (int k = 0; k < K; ++k) s[k] = kab_neg_inf();
   if (lane1) s[0] = 0.0f;  // virtual start state 0, score 0 (align.py:57-58)
 
-  // -- emission pipeline: chunk c uses stage (chunk_counter + c) % STAGES
+  // -- emission pipeline: chunk c uses stage (chunk_counter + c) % STAGES.  F * V * 4 is a multiple
+  // of 16, so every chunk of the lattice has the same 16-byte skew and all but the last one are
+  // plain aligned copies of `full_bytes`; only the last chunk goes through the clamping descriptor.
   const uint32_t cc0 = chunk_counter;
+  const int64_t lat_b0 = lat.t_off * (int64_t)V * 4;
+  const char *lp_base = reinterpret_cast<const char *>(p.lp) + (lat_b0 & ~(int64_t)15);
+  const int w0 = (int)((lat_b0 & 15) >> 2);  // word index of a chunk's first value inside its stage
+  const uint32_t chunk_stride = (uint32_t)(F * V * 4);
+  const uint32_t full_bytes = (chunk_stride + (uint32_t)w0 * 4u + 15u) & ~15u;
+  uint32_t ist = cc0 % KAB_WARP_STAGES;  // stage of the next chunk to issue
   auto issue = [&](int c) {
-    const uint32_t g = cc0 + c, st = g % KAB_WARP_STAGES;
-    const int f0 = c * F, nf = min(F, T - f0);
-    const KabStageDesc d = kab_stage_desc(p, lat.t_off, f0, nf);
-    float *dst = stage_base + st * stage_words;
-    if (lane0) {
-      kab_mbar_expect_tx(&bars[st], d.bytes);
-      if (d.bytes) kab_bulk_g2s_hint(dst, d.src, d.bytes, &bars[st], policy);
+    float *dst = stage_base + ist * stage_words;
+    if (c + 1 < n_chunks) {
+      if (lane0) {
+        kab_mbar_expect_tx(&bars[ist], full_bytes);
+        kab_bulk_g2s_hint(dst, lp_base + (size_t)c * chunk_stride, full_bytes, &bars[ist], policy);
+      }
+    } else {
+      const int f0 = c * F;
+      const KabStageDesc d = kab_stage_desc(p, lat.t_off, f0, T - f0);
+      if (lane0) {
+        kab_mbar_expect_tx(&bars[ist], d.bytes);
+        if (d.bytes) kab_bulk_g2s_hint(dst, d.src, d.bytes, &bars[ist], policy);
+      }
+      if (lane < (int)d.tail_n)  // last (< 16 B) words of the whole log_probs buffer
+        dst[d.tail_word + lane] = __ldg(reinterpret_cast<const float *>(d.src) + d.tail_word + lane);
     }
-    if (lane < (int)d.tail_n)  // last (< 16 B) words of the whole log_probs buffer
-      dst[d.tail_word + lane] = __ldg(reinterpret_cast<const float *>(d.src) + d.tail_word + lane);
+    ist = ist + 1 == KAB_WARP_STAGES ? 0 : ist + 1;
   };
   const int pre = min(n_chunks, KAB_WARP_STAGES - 1);
   for (int c = 0; c < pre; ++c) issue(c);
 
   float poison = 0.0f;  // NaN once a non-finite log-prob was staged (kab_poison)
   uint32_t *bprow = bpw + lane;  // this lane's slot in the current word-row
+  uint32_t st = cc0 % KAB_WARP_STAGES, ph = (cc0 / KAB_WARP_STAGES) & 1u;  // stage / phase of the chunk being read
   for (int c = 0; c < n_chunks; ++c) {
     // the stage consumed in iteration c-1 is free again: refill it with chunk c + STAGES - 1
     __syncwarp();
     // (every LDS of that stage has completed: its values were consumed by the frame updates
     // this warp has already issued, so the bulk copy cannot overtake a pending read)
     if (c + KAB_WARP_STAGES - 1 < n_chunks) issue(c + KAB_WARP_STAGES - 1);
-    const uint32_t g = cc0 + c, st = g % KAB_WARP_STAGES;
-    kab_mbar_wait(&bars[st], (g / KAB_WARP_STAGES) & 1u);
+    kab_mbar_wait(&bars[st], ph);
     __syncwarp();
-    const int f0 = c * F, nf = min(F, T - f0);
+    const int nf = min(F, T - c * F);
     const float *stage = stage_base + st * stage_words;
-    const int w0 = (int)((((lat.t_off + f0) * (int64_t)V * 4) & 15) >> 2), w1 = w0 + nf * V;
+    if (++st == KAB_WARP_STAGES) { st = 0; ph ^= 1u; }
+    const int w1 = w0 + nf * V;
     {  // finiteness of exactly this lattice's words [w0, w1) of the stage
       const int v0 = (w0 + 3) >> 2, v1 = w1 >> 2;
       const float4 *s4 = reinterpret_cast<const float4 *>(stage);
