@@ -37,7 +37,8 @@ constexpr int N_QUEUES = 3;
 constexpr int Q_WARP = 0, Q_BAND = 1, Q_GENERIC = 2;
 constexpr int BAND_MAX_WARPS = 32;
 constexpr int GENERIC_NT = 256;
-constexpr int MAX_STAGE_V = 128;  // widest vocabulary the staged (warp / band) kernels take
+constexpr int MAX_STAGE_V = 512;  // widest vocabulary the staged (warp / band) kernels take: whole rows
+                                  // are staged, 8 frames x 2 KB x 3 stages x 4 warps = 197 KB per CTA at V = 512
 
 inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
@@ -244,7 +245,7 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
     const int nc = (pl->band_nw + KAB_BP_CW - 1) / KAB_BP_CW;
     const char *cl = getenv("KAB_BAND_CLUSTER");
     const int want_nc = cl ? atoi(cl) : 0;
-    if (nc <= 8 && want_nc >= 1) {
+    if (nc <= 8 && want_nc >= 1 && kab_bandp_geom(pl->stage_bytes).smem_bytes <= 227 * 1024) {
       pl->band_nc = std::min(8, std::max(nc, want_nc));
       for (KabLattice &d : pl->lists[Q_BAND]) {
         d.bp_off = bp_bytes;

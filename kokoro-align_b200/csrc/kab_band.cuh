@@ -1,5 +1,5 @@
 // kab_band.cuh -- one CTA per lattice, for chapter-length lattices with the reference's
-// diagonal band (align.py:64-65): max_move = 4, labels in 1..V-1, V <= 128, S <= 3T,
+// diagonal band (align.py:64-65): max_move = 4, labels in 1..V-1, V <= 512, S <= 3T,
 // min(beam_size, S) + 32 <= R where R = 104 * NW ring slots (NW warps, NW <= 32).
 //
 //   * state v lives in ring slot v mod R.  Warp w OWNS slots 104w .. 104w+103: lanes 6..31 hold

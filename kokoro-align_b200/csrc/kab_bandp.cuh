@@ -1,6 +1,6 @@
 // kab_bandp.cuh -- chapter-length lattices with the reference's diagonal band (align.py:64-65),
 // one thread-block CLUSTER per lattice, every warp on its own SM sub-partition, no barrier on
-// the recurrence.  Same shapes as kab_band.cuh (max_move = 4, labels in 1..V-1, V <= 128,
+// the recurrence.  Same shapes as kab_band.cuh (max_move = 4, labels in 1..V-1, V <= 512,
 // S <= 3T) with min(beam_size, S) + 32 <= R = 104 * NWT ring slots, NWT = 4 * NC compute warps
 // in a cluster of NC <= 8 CTAs.
 //

@@ -1,6 +1,6 @@
 // kab_warp.cuh -- one WARP per lattice, for the silence-split short segments of BASELINE
 // config 2 (S = 2L+1 <= 248, window never clips: lo_i = 0, hi_i = S for every frame,
-// max_move = 4, labels in 1..V-1, V <= 128).
+// max_move = 4, labels in 1..V-1, V <= 512).
 //
 //   * state row lives in registers: lane l >= 1 owns states K*(l-1) .. K*l-1 (K = 2,4,6,8 even,
 //     so even register index == blank state; lane 0 is an all -inf dummy that feeds lane 1's

@@ -201,3 +201,18 @@ def test_cluster_band_kernel(kab, monkeypatch, beam_size, cluster):
     lp, t_off, labels, l_off = synth.make_batch(T, L, seed=4300 + beam_size, planted=True)
     info = _compare_batch(kab, lp, t_off, labels, l_off, beam_size=beam_size)
     assert info.n_class[1] >= 4
+
+
+@pytest.mark.parametrize("V", [128, 256, 512, 600])
+def test_wide_vocabularies(kab, V):
+    """Vocabularies up to 512 columns run in the staged warp / band kernels (whole rows staged),
+    wider ones in the generic kernel; all bit-exact against the C oracle."""
+    from kokoro_align_b200 import synth
+    T = np.array([700, 90, 3000, 431])
+    L = np.array([100, 12, 800, 60])
+    lp, t_off, labels, l_off = synth.make_batch(T, L, V=V, seed=5100 + V, planted=True)
+    info = _compare_batch(kab, lp, t_off, labels, l_off, beam_size=300, V=V)
+    if V <= 512:
+        assert info.n_class[0] == 2 and info.n_class[1] == 2
+    else:
+        assert info.n_class[2] == 4
