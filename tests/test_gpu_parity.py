@@ -216,3 +216,25 @@ def test_wide_vocabularies(kab, V):
         assert info.n_class[0] == 2 and info.n_class[1] == 2
     else:
         assert info.n_class[2] == 4
+
+
+def test_config4_banded_million_frames(kab):
+    """BASELINE config 4(i): ONE lattice of T = 10^6 frames, L = 50 000 labels, the default
+    1000-wide band (10^9 evaluated cells), bit-exact against the C oracle; then the same batch
+    entry with a second, shorter lattice behind it (offsets beyond 2^31 bytes of log-probs are
+    not reached here, but T * V * 4 = 156 MB exercises the 64-bit row arithmetic)."""
+    from kokoro_align_b200 import synth
+    from oracle import ctc_oracle
+    T, L = 1_000_000, 50_000
+    lp, t_off, labels, l_off = synth.make_batch_fast(np.array([T, 4097]), np.array([L, 600]), seed=4004)
+    rp, rl, rs, rf, rst = ctc_oracle.ctc_best_path_batch(lp, t_off, labels, l_off, n_threads=2)
+    assert (rst == 0).all()
+    with kab.AlignPlan(t_off, labels, l_off, 39) as plan:
+        path, labs, scores, final, status = plan.run_host(lp)
+        assert plan.info.n_class[1] == 2
+    assert (status == 0).all()
+    np.testing.assert_array_equal(path, rp)
+    np.testing.assert_array_equal(labs, rl)
+    assert scores.tobytes() == rs.tobytes() and final.tobytes() == rf.tobytes()
+    d = np.diff(path[:T])
+    assert d.min() >= 0 and d.max() <= 3
