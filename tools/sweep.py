@@ -19,15 +19,18 @@ peak = 6538.6
 if os.path.exists("MEASURED_PEAKS.json"):
     peak = json.load(open("MEASURED_PEAKS.json"))["hbm_gbs"]
 out = []
-for T in Ts:
-    for L in Ls:
+points = [(T, L, 39) for T in Ts for L in Ls]
+# wide vocabularies (whole rows are staged up to V = 512; V = 4096 runs in the generic kernel)
+points += [(1000, 100, 256), (10000, 1000, 256), (1000, 100, 512)] + ([] if quick else [(1000, 100, 4096)])
+for T, L, V in points:
+    if True:
         S = 2 * L + 1
         if S > 2 * T:
             continue
-        frames_budget = 6_000_000          # keep inputs below ~1 GB per point
+        frames_budget = 6_000_000 * 39 // V          # keep inputs below ~1 GB per point
         B = int(max(1, min(4096, frames_budget // T)))
-        lp, t_off, labels, l_off = synth.make_batch_fast(np.full(B, T), np.full(B, L), seed=5000 + T % 97 + L % 89)
-        plan = align.AlignPlan(t_off, labels, l_off, 39)
+        lp, t_off, labels, l_off = synth.make_batch_fast(np.full(B, T), np.full(B, L), V=V, seed=5000 + T % 97 + L % 89)
+        plan = align.AlignPlan(t_off, labels, l_off, V)
         d_lp = torch.from_numpy(lp).cuda()
         for _ in range(2):
             o = plan.run_torch(d_lp)
@@ -39,11 +42,11 @@ for T in Ts:
             best = min(best, e0.elapsed_time(e1))
         st = o[4].cpu().numpy()
         info = plan.info
-        rec = dict(T=T, L=L, S=S, B=B, V=39, beam_size=1000, ms=best, status_ok=bool((st == 0).all()),
+        rec = dict(T=T, L=L, S=S, B=B, V=V, beam_size=1000, ms=best, status_ok=bool((st == 0).all()),
                    cells_eval=int(info.cells_eval), cells_nominal=int(info.cells_nominal),
                    cells_eval_per_s=info.cells_eval / best * 1e3, cells_nominal_per_s=info.cells_nominal / best * 1e3,
                    algorithmic_gbs=info.algorithmic_bytes / best / 1e6, hbm_frac=info.algorithmic_bytes / best / 1e6 / peak,
-                   ns_per_frame=best * 1e6 / T, classes=list(info.n_class))
+                   ns_per_frame=best * 1e6 / T, lp_gbs=lp.nbytes / best / 1e6, classes=list(info.n_class))
         out.append(rec)
         print(json.dumps(rec), file=sys.stderr, flush=True)
         plan.close()
