@@ -181,6 +181,52 @@ def best_path(input_file, voca_file, output_file):
     np.savez(output_file, best_path=path, best_labels=labs, best_scores=scores)
 
 
+def best_path_files(logits_files, voca_files, best_path_files, skip_existing=True, beam_size=1000,
+                    max_move=4, verbose=True):
+    """The per-book loop of run_example.py:247-254 as ONE batch: every chapter whose output does
+    not exist yet is loaded, normalised (align.py:116-117), and all of them are aligned in a single
+    plan -- the chapters are independent lattices, so they run side by side on the GPU (36
+    chapters of a 9-hour book take the time of the longest one).  Writes the same best_path.npz
+    files, prints the reference's two messages, and raises the reference's exception for the first
+    chapter that fails (after the other chapters have been written).  Returns the written paths.
+
+    Under torch.distributed (one process per GPU) the chapters are sharded over the ranks by
+    cost (parallel.align_sharded: no collective on the data path, a host-side gather of the
+    results) and rank 0 writes the files."""
+    import os
+    todo = []
+    for lf, vf, bf in zip(logits_files, voca_files, best_path_files):
+        if skip_existing and os.path.exists(bf):
+            if verbose:
+                print(f'Skip writing {bf}')
+        else:
+            todo.append((lf, vf, bf))
+    if not todo:
+        return []
+    lps, labs = [], []
+    for lf, vf, _ in todo:
+        with np.load(lf) as f:
+            lps.append(np.ascontiguousarray(log_softmax(f['data']), dtype=np.float32))
+        labs.append(np.asarray(read_transcript_labels(vf), dtype=np.int32))
+    from . import parallel
+    V = lps[0].shape[1]
+    results = parallel.align_sharded(lps, labs, beam_size=beam_size, max_move=max_move,
+                                     device=_current_device())
+    if results is None:  # not the gathering rank
+        return []
+    written, first_bad = [], ST_OK
+    for (_, _, bf), (path, lab, sc, _, st) in zip(todo, results):
+        if st != ST_OK:
+            first_bad = first_bad or st
+            continue
+        if verbose:
+            print(f'Writing {bf}')
+        np.savez(bf, best_path=path, best_labels=lab, best_scores=sc)
+        written.append(bf)
+    raise_for_status(first_bad, V)
+    return written
+
+
 # --------------------------------------------------------------------------- the consumer
 # SURVEY.md 8(f) rank 1: the step that reads best_path.npz (align.py:127-169).  Host-side text
 # work; it defines the output contract of the kernels (best_path // 2 at the segment

@@ -238,3 +238,30 @@ def test_config4_banded_million_frames(kab):
     assert scores.tobytes() == rs.tobytes() and final.tobytes() == rf.tobytes()
     d = np.diff(path[:T])
     assert d.min() >= 0 and d.max() <= 3
+
+
+def test_best_path_files_batch(kab, tmp_path, capsys):
+    """The per-book loop (run_example.py:247-254) as one batch: same npz files as the per-file
+    best_path(), existing outputs skipped with the reference's message."""
+    rng = np.random.default_rng(77)
+    logits_files, voca_files, out_files, ref_files = [], [], [], []
+    for n, (T, nl) in enumerate(((900, 9), (2600, 40), (130, 1))):
+        lf, vf = tmp_path / f"c{n}.logits.npz", tmp_path / f"c{n}.voca.txt"
+        np.savez(lf, data=rng.standard_normal((T, 39)).astype(np.float32) * 3, indices=np.array([T], np.int32))
+        with open(vf, "w") as f:
+            for k in range(nl):
+                f.write(f"text {k}|k o k o r o , w a t a sh i\\n")
+        logits_files.append(str(lf)); voca_files.append(str(vf))
+        out_files.append(str(tmp_path / f"c{n}.best_path.npz")); ref_files.append(str(tmp_path / f"c{n}.ref.npz"))
+    for lf, vf, rf in zip(logits_files, voca_files, ref_files):
+        kab.best_path(lf, vf, rf)
+    np.savez(out_files[2], best_path=np.zeros(1, np.int32))  # already there: must be skipped
+    written = kab.best_path_files(logits_files, voca_files, out_files)
+    out = capsys.readouterr().out
+    assert written == out_files[:2]
+    assert f"Skip writing {out_files[2]}" in out and f"Writing {out_files[0]}" in out
+    for of, rf in zip(out_files[:2], ref_files[:2]):
+        with np.load(of) as a, np.load(rf) as b:
+            assert sorted(a.files) == ["best_labels", "best_path", "best_scores"]
+            for key in a.files:
+                assert a[key].dtype == b[key].dtype and a[key].tobytes() == b[key].tobytes()
