@@ -87,13 +87,7 @@ __device__ __forceinline__ void kab_bulk_g2s(void *dst, const void *src, uint32_
                "l"(src), "r"(bytes), "r"(kab_smem_u32(bar))
                : "memory");
 }
-// Same, with an L2 eviction-priority hint: emission rows are read exactly once, so they are
-// fetched evict-first and do not push the (re-read) backpointer rows out of L2.
-__device__ __forceinline__ uint64_t kab_policy_evict_first() {
-  uint64_t pol;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-  return pol;
-}
+// Same, with an L2 eviction-priority hint (createpolicy); the warp kernel passes evict_normal.
 __device__ __forceinline__ void kab_bulk_g2s_hint(void *dst, const void *src, uint32_t bytes, uint64_t *bar,
                                                   uint64_t policy) {
   asm volatile(
