@@ -51,12 +51,13 @@ extern "C" {
 #define KAB_CLASS_WARP 0    /* one warp per lattice, full window, S <= 248, max_move 4 */
 #define KAB_CLASS_BAND 1    /* one CTA per lattice, ring of >= beam_size+12 states in registers, max_move 4 */
 #define KAB_CLASS_GENERIC 2 /* any beam_size / max_move / label values */
+#define KAB_CLASS_WIDE 3    /* unbanded lattice too wide for one CTA: a chain of warps over the whole GPU */
 
 typedef struct kab_plan kab_plan; /* opaque */
 
 typedef struct kab_plan_info {
   int64_t n_lattices;
-  int64_t n_class[3];       /* lattices per KAB_CLASS_* */
+  int64_t n_class[4];       /* lattices per KAB_CLASS_* */
   int64_t total_frames;     /* sum_b T_b */
   int64_t cells_eval;       /* sum_b sum_i (hi_i - lo_i): cells the recurrence evaluates */
   int64_t cells_nominal;    /* sum_b T_b * S_b */

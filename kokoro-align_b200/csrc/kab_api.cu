@@ -14,6 +14,7 @@
 
 #include "kab_band.cuh"
 #include "kab_bandp.cuh"
+#include "kab_wide.cuh"
 #include "kab_common.cuh"
 #include "kab_generic.cuh"
 #include "kab_warp.cuh"
@@ -33,8 +34,8 @@ int cuda_fail(cudaError_t e, const char *what) {
   } while (0)
 
 // kernel classes (one work queue each)
-constexpr int N_QUEUES = 3;
-constexpr int Q_WARP = 0, Q_BAND = 1, Q_GENERIC = 2;
+constexpr int N_QUEUES = 4;
+constexpr int Q_WARP = 0, Q_BAND = 1, Q_GENERIC = 2, Q_WIDE = 3;
 constexpr int BAND_MAX_WARPS = 32;
 constexpr int GENERIC_NT = 256;
 constexpr int MAX_STAGE_V = 512;  // widest vocabulary the staged (warp / band) kernels take: whole rows
@@ -75,6 +76,8 @@ struct kab_plan {
   float *d_scratch = nullptr;
   unsigned int *d_queue = nullptr;
   int32_t *d_status_init = nullptr;
+  unsigned char *d_wide_ws = nullptr;  // wide kernel: per-lattice control words and neighbour FIFOs
+  int64_t wide_ws_bytes = 0;
   // launch geometry
   int grid[N_QUEUES] = {};
   size_t smem[N_QUEUES] = {};
@@ -102,7 +105,7 @@ int plan_free(kab_plan *pl) {
   cudaSetDevice(pl->device);
   for (int q = 0; q < N_QUEUES; ++q) cudaFree(pl->d_lists[q]);
   cudaFree(pl->d_col16); cudaFree(pl->d_raw); cudaFree(pl->d_bp); cudaFree(pl->d_scratch);
-  cudaFree(pl->d_queue); cudaFree(pl->d_status_init);
+  cudaFree(pl->d_queue); cudaFree(pl->d_status_init); cudaFree(pl->d_wide_ws);
   cudaFree(pl->d_lp); cudaFree(pl->d_path); cudaFree(pl->d_lab); cudaFree(pl->d_st);
   cudaFree(pl->d_sc); cudaFree(pl->d_fs);
   if (pl->stream) cudaStreamDestroy(pl->stream);
@@ -173,6 +176,19 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
   }
   pl->stage_bytes = (int32_t)align_up((int64_t)pl->stage_frames * V * 4 + 24, 16);
 
+  // resident CTAs of the wide kernel (its warps spin on each other: the whole grid must be resident)
+  int wide_capacity = 0;
+  {
+    const KabWideGeom wgeo = kab_wide_geom(pl->stage_bytes);
+    int occ = 0;
+    if (wgeo.smem_bytes <= 227 * 1024 &&
+        cudaFuncSetAttribute(kab_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wgeo.smem_bytes) == cudaSuccess &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kab_wide_kernel, KAB_WD_THREADS, wgeo.smem_bytes) == cudaSuccess)
+      wide_capacity = occ * pl->sm_count;
+    (void)cudaGetLastError();
+  }
+  int wide_max_ctas = 0;
+
   // ---- classify, build the padded column table (numpy-style wrap of negative labels)
   std::vector<uint16_t> col16;
   std::vector<int32_t> status_init((size_t)B, 0);
@@ -219,6 +235,15 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
     } else if (fast && W >= 1 && S <= 3 * T && weff + 32 <= KAB_BAND_OW * BAND_MAX_WARPS) {
       q = Q_BAND;  // backpointer offsets are assigned below, once the ring size is known
       max_band_weff = std::max(max_band_weff, weff);
+    } else if (fast && full && ((S + KAB_BAND_OW - 1) / KAB_BAND_OW + KAB_WD_CW - 1) / KAB_WD_CW + 1 <= wide_capacity) {
+      q = Q_WIDE;  // unbanded and wider than a CTA: a chain of warps over the whole GPU
+      const int nww = (int)((S + KAB_BAND_OW - 1) / KAB_BAND_OW);
+      d.k = nww;
+      wide_max_ctas = std::max(wide_max_ctas, (nww + KAB_WD_CW - 1) / KAB_WD_CW);
+      d.bp_off = bp_bytes;
+      bp_bytes += (int64_t)nww * ((T + 7) / 8) * 256;  // [warp][group][32 lanes][8 B]
+      d.scr_off = pl->wide_ws_bytes / 4;
+      pl->wide_ws_bytes += (int64_t)align_up((int64_t)kab_wide_ws_bytes(nww), 256);
     } else {
       q = Q_GENERIC;
       d.bp_off = bp_bytes;
@@ -227,7 +252,7 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
       scr_floats += align_up(2 * (S + 16), 64);
     }
     pl->lists[q].push_back(d);
-    info.n_class[q == Q_WARP ? KAB_CLASS_WARP : (q == Q_GENERIC ? KAB_CLASS_GENERIC : KAB_CLASS_BAND)]++;
+    info.n_class[q == Q_WARP ? KAB_CLASS_WARP : (q == Q_GENERIC ? KAB_CLASS_GENERIC : (q == Q_WIDE ? KAB_CLASS_WIDE : KAB_CLASS_BAND))]++;
     const int64_t cells = cells_eval_of(T, S, W);
     info.cells_eval += cells;
     info.cells_nominal += T * S;
@@ -332,13 +357,18 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
       pl->smem[Q_BAND] = geo.smem_bytes;
       pl->grid[Q_BAND] = (int)std::min<int64_t>((int64_t)pl->lists[Q_BAND].size(), (int64_t)pl->sm_count * std::max(occ, 1));
     }
+    if (!pl->lists[Q_WIDE].empty()) {
+      if ((e = cudaMalloc((void **)&pl->d_wide_ws, (size_t)pl->wide_ws_bytes)) != cudaSuccess) { rc = cuda_fail(e, "cudaMalloc(wide workspace)"); break; }
+      pl->smem[Q_WIDE] = kab_wide_geom(pl->stage_bytes).smem_bytes;
+      pl->grid[Q_WIDE] = wide_max_ctas + 1;  // forward CTAs + the backtrack CTA
+    }
     if (!pl->lists[Q_GENERIC].empty())
       pl->grid[Q_GENERIC] = (int)std::min<int64_t>((int64_t)pl->lists[Q_GENERIC].size(), (int64_t)pl->sm_count * 4);
   } while (0);
   if (rc != KAB_OK) { plan_free(pl); return rc; }
 
   info.backptr_bytes = bp_bytes;
-  info.workspace_bytes = bp_bytes + scr_floats * 4 + (int64_t)col16.size() * 2 +
+  info.workspace_bytes = bp_bytes + scr_floats * 4 + pl->wide_ws_bytes + (int64_t)col16.size() * 2 +
                          (pl->d_raw ? pl->total_L * 4 : 0) + B * (int64_t)sizeof(KabLattice);
   info.kernel_launches = 0;
   for (int q = 0; q < N_QUEUES; ++q) info.kernel_launches += pl->lists[q].empty() ? 0 : 1;
@@ -444,6 +474,38 @@ int kab_plan_run_device(kab_plan *pl, const float *d_log_probs, int32_t *d_best_
                 h[w * 8 + 0], h[w * 8 + 1], h[w * 8 + 2], h[w * 8 + 3], h[w * 8 + 4], h[w * 8 + 5], h[w * 8 + 6], h[w * 8 + 7]);
     }
 #endif
+  }
+  if (!pl->lists[Q_WIDE].empty()) {
+    KAB_CUDA(cudaMemsetAsync(pl->d_wide_ws, 0, (size_t)pl->wide_ws_bytes, stream));
+#ifdef KAB_WIDE_TIMING
+    static long long *wdbg2 = nullptr;
+    if (!wdbg2) cudaMalloc((void **)&wdbg2, 64 * sizeof(long long));
+    cudaMemsetAsync(wdbg2, 0, 64 * sizeof(long long), stream);
+    p.debug = wdbg2;
+    struct WideDbgPrint {
+      long long *d; cudaStream_t s;
+      ~WideDbgPrint() {
+        long long h[64];
+        cudaStreamSynchronize(s);
+        cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+        const char *nm[6] = {"w0", "w1", "w2", "w3", "mid", "last"};
+        for (int w = 0; w < 6; ++w) {
+          const long long *x = h + w * 8;
+          const double n = (double)(x[7] ? x[7] : 1);
+          fprintf(stderr, "%4s: per group: ghost %6.0f emis %5.0f comp %6.0f pub %6.0f rest %5.0f | prefetch misses %lld of %lld groups, total %lld cyc\n",
+                  nm[w], x[0] / n, x[1] / n, x[2] / n, x[3] / n, x[4] / n, x[5], x[7], x[6]);
+        }
+      }
+    } wdbg_print{wdbg2, stream};
+#endif
+    // cooperative launch: the warps of the chain spin on each other, so the whole grid has to be
+    // resident -- the runtime checks that instead of letting the kernel hang
+    const KabLattice *wl = pl->d_lists[Q_WIDE];
+    int wn = (int)pl->lists[Q_WIDE].size();
+    unsigned char *wws = pl->d_wide_ws;
+    void *wargs[] = {(void *)&wl, (void *)&wn, (void *)&p, (void *)&wws};
+    KAB_CUDA(cudaLaunchCooperativeKernel((const void *)kab_wide_kernel, dim3((unsigned)pl->grid[Q_WIDE]),
+                                         dim3(KAB_WD_THREADS), wargs, pl->smem[Q_WIDE], stream));
   }
   if (!pl->lists[Q_GENERIC].empty()) {
     KabParams pg = p; pg.queue = pl->d_queue + Q_GENERIC;

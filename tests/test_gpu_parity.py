@@ -265,3 +265,17 @@ def test_best_path_files_batch(kab, tmp_path, capsys):
             assert sorted(a.files) == ["best_labels", "best_path", "best_scores"]
             for key in a.files:
                 assert a[key].dtype == b[key].dtype and a[key].tobytes() == b[key].tobytes()
+
+
+@pytest.mark.parametrize("T,L", [(3000, 2500), (1003, 1500), (5, 300), (2047, 4000)])
+def test_wide_unbanded_lattices(kab, T, L):
+    """Unbanded lattices wider than one CTA (beam_size >= 2S: BASELINE config 4(ii) shape, small):
+    the chain-of-warps kernel (kab_wide.cuh) against the C oracle, bit for bit; a second lattice
+    behind the first one exercises the lattice loop and the backtrack CTA's hand-over."""
+    from kokoro_align_b200 import synth
+    Ts = np.array([T, max(3, T // 2), 700])
+    Ls = np.array([L, L + 37, 2000])
+    lp, t_off, labels, l_off = synth.make_batch(Ts, Ls, seed=6000 + T, planted=(T > 100))
+    beam = 2 * (2 * int(Ls.max()) + 1) + 2
+    info = _compare_batch(kab, lp, t_off, labels, l_off, beam_size=beam)
+    assert info.n_class[3] >= 2 and info.n_class[2] == 0
