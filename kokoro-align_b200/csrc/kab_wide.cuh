@@ -42,6 +42,9 @@
 #define KAB_WD_D 64      // neighbour FIFO depth (messages).  Deep on purpose: a consumer that has fallen two
 #endif                  // groups behind finds every message prefetched and never blocks again; with 8 slots the
                         // credits keep pulling it back into blocking polls (measured: 55 ms -> 24 ms at D = 64)
+#ifndef KAB_WD_LAG
+#define KAB_WD_LAG 2     // a warp starts once its lower neighbour has finished this many groups, so that
+#endif                   // every later message is already there when it is prefetched (a group early)
 #define KAB_WD_FBW 64    // frames per per-warp backpointer block
 #define KAB_WD_FBK 128   // frames per backtrack block
 #define KAB_WD_NREG 3    // warp regions staged per backtrack block
@@ -72,20 +75,20 @@ __host__ __device__ inline KabWideGeom kab_wide_geom(int stage_bytes) {
 }
 
 __device__ __forceinline__ void kab_st_volatile_b64(void *p, uint32_t lo, uint32_t hi) {
-  asm volatile("st.volatile.global.v2.b32 [%0], {%1, %2};" ::"l"(p), "r"(lo), "r"(hi) : "memory");
+  asm volatile("st.relaxed.gpu.global.v2.b32 [%0], {%1, %2};" ::"l"(p), "r"(lo), "r"(hi) : "memory");
 }
 __device__ __forceinline__ uint2 kab_ld_volatile_b64(const void *p) {
   uint2 v;
-  asm volatile("ld.volatile.global.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ uint32_t kab_ld_volatile_u32(const void *p) {
   uint32_t v;
-  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ void kab_st_volatile_u32(void *p, uint32_t v) {
-  asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 // Grid: n_fwd forward CTAs + 1 backtrack CTA (the last one), all resident.  Every CTA runs over the
@@ -244,6 +247,13 @@ __global__ void __launch_bounds__(KAB_WD_THREADS, 1)
           s0 = n0; s1 = m1; s2 = m2; s3 = m3;
         };
 
+        // ---- build the wavefront: wait until the warp below is KAB_WD_LAG groups ahead (its message
+        // KAB_WD_LAG - 1 has landed); both then run at the same pace and the lag stays
+        if (has_below && n_groups - 1 >= KAB_WD_LAG && !owned) {
+          const unsigned char *slot = inbox + (size_t)((KAB_WD_LAG - 1) % D) * KAB_WD_MSG_BYTES;
+          while (kab_ld_volatile_b64(slot + 24).y != (uint32_t)KAB_WD_LAG) __nanosleep(64);
+        }
+        __syncwarp();
 #ifdef KAB_WIDE_TIMING
         long long tm_ghost = 0, tm_emis = 0, tm_comp = 0, tm_pub = 0, tm_rest = 0, n_miss = 0;
         const long long tm_start = clock64();

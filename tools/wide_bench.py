@@ -10,8 +10,11 @@ for T, L in shapes:
     d = torch.from_numpy(lp).cuda()
     o = plan.run_torch(d); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(); o = plan.run_torch(d); e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
+    times = []
+    for _ in range(3):
+        e0.record(); o = plan.run_torch(d); e1.record(); torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    ms = min(times)
     st = o[4].cpu().numpy()
-    print(f"T={T} L={L} S={S} unbanded: {ms:.2f} ms, {plan.info.cells_eval/ms/1e6:.1f} Gcells/s, bp {plan.info.backptr_bytes/1e9:.2f} GB, alg GB/s {plan.info.algorithmic_bytes/ms/1e6:.0f}, status {st}, classes {list(plan.info.n_class)}", flush=True)
+    print(f"T={T} L={L} S={S} unbanded: {ms:.2f} ms (3 runs: {", ".join("%.1f" % t for t in times)}), {plan.info.cells_eval/ms/1e6:.1f} Gcells/s, bp {plan.info.backptr_bytes/1e9:.2f} GB, alg GB/s {plan.info.algorithmic_bytes/ms/1e6:.0f}, status {st}, classes {list(plan.info.n_class)}", flush=True)
     plan.close(); del d
