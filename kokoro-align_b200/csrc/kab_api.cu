@@ -78,6 +78,8 @@ struct kab_plan {
   int32_t *d_status_init = nullptr;
   unsigned char *d_wide_ws = nullptr;  // wide kernel: per-lattice control words and neighbour FIFOs
   int64_t wide_ws_bytes = 0;
+  unsigned char *d_band_fifo = nullptr;  // cluster band kernel: per-lattice progress counters and FIFOs
+  int64_t band_fifo_bytes = 0;
   // launch geometry
   int grid[N_QUEUES] = {};
   size_t smem[N_QUEUES] = {};
@@ -105,7 +107,7 @@ int plan_free(kab_plan *pl) {
   cudaSetDevice(pl->device);
   for (int q = 0; q < N_QUEUES; ++q) cudaFree(pl->d_lists[q]);
   cudaFree(pl->d_col16); cudaFree(pl->d_raw); cudaFree(pl->d_bp); cudaFree(pl->d_scratch);
-  cudaFree(pl->d_queue); cudaFree(pl->d_status_init); cudaFree(pl->d_wide_ws);
+  cudaFree(pl->d_queue); cudaFree(pl->d_status_init); cudaFree(pl->d_wide_ws); cudaFree(pl->d_band_fifo);
   cudaFree(pl->d_lp); cudaFree(pl->d_path); cudaFree(pl->d_lab); cudaFree(pl->d_st);
   cudaFree(pl->d_sc); cudaFree(pl->d_fs);
   if (pl->stream) cudaStreamDestroy(pl->stream);
@@ -263,18 +265,29 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
   }
   if (!pl->lists[Q_BAND].empty()) {
     pl->band_nw = (int32_t)((max_band_weff + 32 + KAB_BAND_OW - 1) / KAB_BAND_OW);
-    // KAB_BAND_CLUSTER=N (N >= 1) selects the pipelined cluster kernel (kab_bandp.cuh: rings of 4 * NC
-    // warps over a cluster of NC <= 8 CTAs, NC = max(N, what the band needs)).  It is bit-exact
-    // and tested, but on B200 it only matches the single-CTA kernel, so
-    // the single-CTA kernel stays the default.
+    // Two band kernels.  The pipelined cluster kernel (kab_bandp.cuh: rings of 4 * NC warps over a
+    // cluster of NC <= 8 CTAs, one warp per scheduler) has the shorter frame (Gon gitsune 14.2 vs
+    // 15.4 ms, config 4(i) 168 vs 188 ms) but takes NC whole SMs per lattice; the single-CTA kernel
+    // (kab_band.cuh) runs two lattices per SM.  So: the cluster kernel when every band lattice of
+    // the plan gets its own cluster at once, the single-CTA kernel for larger batches.
+    // KAB_BAND_CLUSTER=0 forces the single-CTA kernel, =N (>= 1) the cluster kernel with >= N CTAs.
     const int nc = (pl->band_nw + KAB_BP_CW - 1) / KAB_BP_CW;
     const char *cl = getenv("KAB_BAND_CLUSTER");
-    const int want_nc = cl ? atoi(cl) : 0;
-    if (nc <= 8 && want_nc >= 1 && kab_bandp_geom(pl->stage_bytes).smem_bytes <= 227 * 1024) {
+    int want_nc = cl ? atoi(cl) : -1;
+    const bool cluster_ok = nc <= 8 && kab_bandp_geom(pl->stage_bytes).smem_bytes <= 227 * 1024;
+    if (want_nc < 0 && cluster_ok) {
+      // resident clusters of this size: every SM holds one CTA of the cluster kernel
+      const int64_t resident = pl->sm_count / nc;
+      want_nc = (int64_t)pl->lists[Q_BAND].size() <= resident ? nc : 0;
+    }
+    if (cluster_ok && want_nc >= 1) {
       pl->band_nc = std::min(8, std::max(nc, want_nc));
+      const int nwt = KAB_BP_CW * pl->band_nc;
       for (KabLattice &d : pl->lists[Q_BAND]) {
         d.bp_off = bp_bytes;
-        bp_bytes += (int64_t)((d.T + 7) / 8) * 256 * KAB_BP_CW * pl->band_nc;  // [warp][group][32 lanes][8 B]
+        bp_bytes += (int64_t)((d.T + 7) / 8) * 256 * nwt;  // [warp][group][32 lanes][8 B]
+        d.scr_off = pl->band_fifo_bytes / 4;
+        pl->band_fifo_bytes += (int64_t)align_up((int64_t)kab_bandp_ws_bytes(nwt), 256);
       }
     } else {
       const KabBandGeom geo = kab_band_geom(pl->band_nw, pl->stage_bytes);
@@ -333,6 +346,7 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
       pl->grid[Q_WARP] = (int)std::min<int64_t>(ctas, (int64_t)pl->sm_count * std::max(occ, 1));
     }
     if (!pl->lists[Q_BAND].empty() && pl->band_nc > 0) {
+      if ((e = cudaMalloc((void **)&pl->d_band_fifo, (size_t)pl->band_fifo_bytes)) != cudaSuccess) { rc = cuda_fail(e, "cudaMalloc(band FIFOs)"); break; }
       const KabBandpGeom geo = kab_bandp_geom(pl->stage_bytes);
       if ((e = cudaFuncSetAttribute(kab_bandp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)geo.smem_bytes)) != cudaSuccess) { rc = cuda_fail(e, "cudaFuncSetAttribute(bandp)"); break; }
       pl->smem[Q_BAND] = geo.smem_bytes;
@@ -368,7 +382,7 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
   if (rc != KAB_OK) { plan_free(pl); return rc; }
 
   info.backptr_bytes = bp_bytes;
-  info.workspace_bytes = bp_bytes + scr_floats * 4 + pl->wide_ws_bytes + (int64_t)col16.size() * 2 +
+  info.workspace_bytes = bp_bytes + scr_floats * 4 + pl->wide_ws_bytes + pl->band_fifo_bytes + (int64_t)col16.size() * 2 +
                          (pl->d_raw ? pl->total_L * 4 : 0) + B * (int64_t)sizeof(KabLattice);
   info.kernel_launches = 0;
   for (int q = 0; q < N_QUEUES; ++q) info.kernel_launches += pl->lists[q].empty() ? 0 : 1;
@@ -425,6 +439,8 @@ int kab_plan_run_device(kab_plan *pl, const float *d_log_probs, int32_t *d_best_
     pb.debug = dbg;
 #endif
     if (pl->band_nc > 0) {
+      KAB_CUDA(cudaMemsetAsync(pl->d_band_fifo, 0, (size_t)pl->band_fifo_bytes, stream));
+      pb.fifo = pl->d_band_fifo;
 #ifdef KAB_BANDP_TIMING
       static long long *pdbg = nullptr;
       if (!pdbg) cudaMalloc((void **)&pdbg, (32 * 16 + 8) * sizeof(long long));

@@ -12,12 +12,15 @@
 //     ghost lanes that recompute the lower neighbour's top 24 states for 8 frames (same scheme
 //     and same exactness argument as kab_band.cuh);
 //   * there is NO group barrier.  After each 8-frame group a warp hands its top six lanes to
-//     the warp above through a 4-deep FIFO in that warp's shared memory: six 16-byte st.async
-//     stores (DSMEM when the neighbour sits in another CTA) that complete_tx on the slot's
-//     mbarrier -- no fence anywhere (a release store costs a MEMBAR.ALL.GPU per group); the
-//     consumer returns the slot with a relaxed remote mbarrier arrive.  A warp at group g only
-//     needs its neighbour's group g-1, so the dependence always points back in time: no
-//     deadlock;
+//     the warp above through a FIFO in GLOBAL memory (L2): every score is stored together with
+//     the message's sequence number as one 8-byte store (single-copy atomic), so there is no
+//     fence, no flag and no mbarrier on the recurrence; the consumer's ghost lanes load message
+//     g at the start of group g and check it at the start of group g+1 (kab_wide.cuh uses the
+//     same scheme).  The first version used st.async + mbarriers over DSMEM: every mbarrier
+//     round trip costs a lone warp 100-250 cycles and the ring ran in lockstep.
+//     A warp whose 24 ghost states are outside the window does not look at its messages at all,
+//     so the ring is a chain whose head runs free, and a warp that (re)joins the chain first
+//     waits until its neighbour is two groups ahead: the wavefront that hides the L2 latency;
 //   * emission rows are staged per CTA by the producer warp: an 8-stage ring of 1-D bulk
 //     copies with full (complete_tx) / empty (4 arrivals) mbarriers, so the four compute warps
 //     may be several groups apart;
@@ -38,23 +41,20 @@
 
 #define KAB_BP_CW 4      // compute warps per CTA
 #define KAB_BP_NS 16     // emission stages per CTA (the four warps of a CTA may be ~12 groups apart)
-#define KAB_BP_D 32      // neighbour FIFO depth (messages): bounds how far the head of the chain runs ahead
+#define KAB_BP_D 64      // neighbour FIFO depth (messages, global memory)
+#define KAB_BP_LAG 2     // a warp joining the chain waits until its lower neighbour is this many groups ahead
 #define KAB_BP_FBW 256   // frames per per-warp backpointer block
 #define KAB_BP_FBK 128   // frames per backtrack block
 #define KAB_BP_NREG 3    // warp regions staged per backtrack block
-#define KAB_BP_FULL_OFF (KAB_BP_D * 96)               // full[D] mbarriers after data[D][6] float4
-#define KAB_BP_EMPTY_OFF (KAB_BP_FULL_OFF + KAB_BP_D * 8)
-#define KAB_BP_FIFO_BYTES (KAB_BP_EMPTY_OFF + KAB_BP_D * 8)  // per compute warp
+#define KAB_BP_MSG_BYTES (KAB_BAND_GHOST * 32)  // 6 lanes x 4 (score, seq) pairs
 #define KAB_BP_THREADS ((KAB_BP_CW + 1) * 32)
 
 struct KabBandpGeom {
-  size_t fifo_off, bpst_off, bt_off, path_off, stage_off, smem_bytes;
+  size_t bpst_off, bt_off, path_off, stage_off, smem_bytes;
 };
 __host__ __device__ inline KabBandpGeom kab_bandp_geom(int stage_bytes) {
   KabBandpGeom g;
-  g.fifo_off = 384;  // after the mbarriers (2 * NS + 2) and the CTA scalars
-  g.bpst_off = g.fifo_off + (size_t)KAB_BP_CW * KAB_BP_FIFO_BYTES;
-  g.bpst_off = (g.bpst_off + 127) & ~(size_t)127;
+  g.bpst_off = 384;  // after the mbarriers (2 * NS + 2) and the CTA scalars
   g.bt_off = g.bpst_off + (size_t)KAB_BP_CW * 2 * KAB_BP_FBW * 32;
   g.path_off = g.bt_off + (size_t)2 * KAB_BP_NREG * KAB_BP_FBK * 32;
   g.stage_off = g.path_off + (size_t)2 * KAB_BP_FBK * 4;
@@ -142,6 +142,66 @@ __device__ __forceinline__ void kab_bulk_wait_read1() {
   asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
 }
 
+// Global scratch of one lattice in cluster mode (zeroed before every run), at p.fifo + lat.scr_off * 4:
+// cons[nwt] (messages warp w is done with), then fifo[nwt][D][192 B]
+__host__ __device__ inline size_t kab_bandp_fifo_off(int nwt) { return ((size_t)nwt * 4 + 255) & ~(size_t)255; }
+__host__ __device__ inline size_t kab_bandp_ws_bytes(int nwt) {
+  return kab_bandp_fifo_off(nwt) + (size_t)nwt * KAB_BP_D * KAB_BP_MSG_BYTES;
+}
+__device__ __forceinline__ void kab_st_volatile_b64(void *p, uint32_t lo, uint32_t hi) {
+  asm volatile("st.relaxed.gpu.global.v2.b32 [%0], {%1, %2};" ::"l"(p), "r"(lo), "r"(hi) : "memory");
+}
+__device__ __forceinline__ uint2 kab_ld_volatile_b64(const void *p) {
+  uint2 v;
+  asm volatile("ld.relaxed.gpu.global.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t kab_ld_volatile_u32(const void *p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void kab_st_volatile_u32(void *p, uint32_t v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Backtrack of ONE full group (8 frames, descending) from registers: w0 holds the 8 backpointer
+// bytes of the walker's byte column, w1 those of the column below (have1: it is available).
+// No load sits on the dependent chain (shift -> mask -> subtract -> compare).  Stops before the
+// frame that would need a third column; returns the next frame to process (-1: group done) and
+// the number of column steps taken (0..2, the last one not yet served when it stopped early).
+__device__ __forceinline__ int kab_walk_group8(const uint2 w0, const uint2 w1, const bool have1, int &v, int &k2,
+                                               int *pg, int &nchg) {
+  // Branch-free on purpose (selects only): with one active thread every taken branch costs a
+  // convergence-barrier round trip (~40 cycles, measured), several times the chain itself.  Frames
+  // after the stop point are computed and discarded (the caller overwrites their path entries).
+  uint32_t cx = w0.x, cy = w0.y;
+  int n = 0, f_next = -1, v_s = 0, k2_s = 0, n_s = 0;
+  bool stopped = false;
+#pragma unroll
+  for (int f = 7; f >= 0; --f) {
+    const uint32_t word = (f >= 4 ? cy : cx) >> (8 * (f & 3));
+    const int mv = (int)((word >> k2) & 3u);
+    pg[f] = v;
+    v -= mv;
+    k2 -= 2 * mv;
+    const bool neg = k2 < 0;  // left the byte column
+    k2 += neg ? 8 : 0;
+    n += neg ? 1 : 0;
+    const bool stop_now = neg && !stopped && (n == 2 || !have1);
+    f_next = stop_now ? f - 1 : f_next;
+    v_s = stop_now ? v : v_s;
+    k2_s = stop_now ? k2 : k2_s;
+    n_s = stop_now ? n : n_s;
+    stopped = stopped || stop_now;
+    cx = neg ? w1.x : cx;
+    cy = neg ? w1.y : cy;
+  }
+  if (stopped) { v = v_s; k2 = k2_s; n = n_s; }
+  nchg = n;
+  return stopped ? f_next : -1;
+}
+
 #ifdef KAB_BANDP_TIMING
 #define KAB_TM(var) const long long var = clock64()
 #define KAB_TM_ADD(acc, a, b) acc += (b) - (a)
@@ -164,7 +224,6 @@ __global__ void __launch_bounds__(KAB_BP_THREADS, 1)
   unsigned int *s_item = reinterpret_cast<unsigned int *>(btbar + 2);
   int *s_vmax = reinterpret_cast<int *>(s_item + 1);
   unsigned int *s_bad = s_item + 2;
-  unsigned char *fifo = kab_smem + geo.fifo_off;
   unsigned char *btbuf = kab_smem + geo.bt_off;                     // [2][NREG][FBK * 32]
   int *pathbuf = reinterpret_cast<int *>(kab_smem + geo.path_off);  // [2][FBK]
   float *stage_base = reinterpret_cast<float *>(kab_smem + geo.stage_off);
@@ -174,20 +233,10 @@ __global__ void __launch_bounds__(KAB_BP_THREADS, 1)
   const int NWT = CW * (int)NC, R = OW * NWT;
   const bool is_prod = warp == CW;
   const int gw = (int)rank * CW + warp;  // global compute-warp index (meaningless for the producer)
-  const int pgw = (gw + NWT - 1) % NWT, ngw = (gw + 1) % NWT;
+  const int ngw = (gw + 1) % NWT;
   const bool owned = lane >= GH;
   const int slot0 = owned ? OW * gw + 4 * (lane - GH) : (OW * gw - 4 * GH + 4 * lane + R) % R;
   const float ninf = kab_neg_inf();
-
-  // Neighbour FIFO.  Block of a compute warp (it is the CONSUMER of the data / full barriers and
-  // the PRODUCER-side owner of the empty barriers):
-  //   data[D][6] float4 | full[D] mbarriers (KAB_BP_FULL_OFF) | empty[D] mbarriers (KAB_BP_EMPTY_OFF)
-  unsigned char *my_blk = fifo + (is_prod ? 0 : warp) * KAB_BP_FIFO_BYTES;
-  const uint32_t my_fifo = kab_smem_u32(my_blk);
-  const uint32_t nxt_fifo =
-      kab_mapa(kab_smem_u32(fifo + (is_prod ? 0 : ngw % CW) * KAB_BP_FIFO_BYTES), is_prod ? rank : (uint32_t)(ngw / CW));
-  const uint32_t prv_fifo =
-      kab_mapa(kab_smem_u32(fifo + (is_prod ? 0 : pgw % CW) * KAB_BP_FIFO_BYTES), is_prod ? rank : (uint32_t)(pgw / CW));
 
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) {
@@ -196,14 +245,10 @@ __global__ void __launch_bounds__(KAB_BP_THREADS, 1)
     }
     kab_mbar_init(&btbar[0], 1);
     kab_mbar_init(&btbar[1], 1);
-    for (int w = 0; w < CW; ++w)
-      for (int j = 0; j < 2 * D; ++j)
-        kab_mbar_init(reinterpret_cast<uint64_t *>(fifo + w * KAB_BP_FIFO_BYTES + KAB_BP_FULL_OFF) + j, 1);
     kab_fence_mbar_init();
   }
   __syncthreads();
   uint32_t echunks = 0;          // emission chunks staged so far by this CTA (same count in every warp)
-  uint32_t msgs = 0;             // neighbour messages so far (same count in every compute warp of the cluster)
   uint32_t bt_uses[2] = {0, 0};  // completed phases of the two backtrack barriers (thread 0)
 
   for (;;) {
@@ -226,7 +271,7 @@ __global__ void __launch_bounds__(KAB_BP_THREADS, 1)
     const uint32_t stage_words = p.stage_bytes >> 2;
     const int n_chunks = (T + F - 1) / F;
     const int n_groups = (T + G - 1) / G;
-    const uint32_t ec0 = echunks, msg0 = msgs;
+    const uint32_t ec0 = echunks;
     const uint32_t skew = (uint32_t)(((lat.t_off * (int64_t)V * 4) & 15) >> 2);
     float s0 = ninf, s1 = ninf, s2 = ninf, s3 = ninf;
     int vb = slot0;
@@ -312,46 +357,42 @@ __global__ void __launch_bounds__(KAB_BP_THREADS, 1)
       int fib = 0, blk = 0;
       uint32_t wlo = 0, whi = 0;  // backpointer bytes of frames 0..3 / 4..7 of the current group
 
-      // One frame; sh = bit offset of this frame's byte in the backpointer word w.
-      auto frame = [&](auto slow_tag, const float xb, const float x1, const float x3, uint32_t &w, const int sh) {
-        constexpr bool SLOW = decltype(slow_tag)::value;
-        int lo = 0, hi = 0;
-        if (SLOW) {
-          lo = max(0, q - half);   // align.py:64
-          hi = min(lo + W, S);     // align.py:65
-          q += qd; r += rd;
-          if (r >= T) { r -= T; ++q; }
-        }
+      // One frame; sh = bit offset of this frame's byte in the backpointer word w.  The window of
+      // align.py:64-65 never appears here: a cell outside [lo, hi) is made inactive through its
+      // EMISSION (-inf: every candidate is -inf, so the maximum is), and the masked emissions of an
+      // edge warp are prepared per group, off the recurrence chain.  xb0 / xb2 are the blank
+      // emissions of this lane's states 0 / 2 (the same value inside the window).
+      auto frame = [&](const float xb0, const float xb2, const float x1, const float x3, uint32_t &w, const int sh) {
         const float h1 = __shfl_up_sync(KAB_FULL_MASK, s3, 1);
         const float h2 = __shfl_up_sync(KAB_FULL_MASK, s2, 1);
         const float h3 = __shfl_up_sync(KAB_FULL_MASK, s1, 1);
-        float t0, t1, t2, t3;
-        kab_add2(s0, s1, xb, t0, t1);
-        kab_add2(s2, s3, xb, t2, t3);
-        const float th1 = __fadd_rn(h1, xb), th3 = __fadd_rn(h3, xb);
+        float t0, t1;
+        kab_add2v(s0, s1, xb0, xb2, t0, t1);  // state 0 <- 0 (move 0), state 2 <- 1 (move 1)
+        const float t2 = __fadd_rn(s2, xb2);
+        const float th1a = __fadd_rn(h1, xb0), th1b = __fadd_rn(h1, xb2), th3 = __fadd_rn(h3, xb0);
         float a0, a1, a2, a3, b0, b1, b2, b3;
         kab_add2(s0, s1, x1, a1, a0);
         kab_add2(h2, h1, x1, a3, a2);
         kab_add2(s2, s3, x3, b1, b0);
         kab_add2(s0, s1, x3, b3, b2);
-        (void)t3;
-        float n0 = kab_blank_sel(t0, th1, th3, w, 1u << (sh + 0), 2u << (sh + 0), one);
-        float m1 = kab_label_sel(a0, a1, a2, a3, w, 1u << (sh + 2), 2u << (sh + 2), one);
-        float m2 = kab_blank_sel(t2, t1, th1, w, 1u << (sh + 4), 2u << (sh + 4), one);
-        float m3 = kab_label_sel(b0, b1, b2, b3, w, 1u << (sh + 6), 2u << (sh + 6), one);
-        if (SLOW) {
-          const unsigned a = (unsigned)(vb - lo), wd = (unsigned)(hi - lo);
-          n0 = (a + 0u < wd) ? n0 : ninf;
-          m1 = (a + 1u < wd) ? m1 : ninf;
-          m2 = (a + 2u < wd) ? m2 : ninf;
-          m3 = (a + 3u < wd) ? m3 : ninf;
-        }
+        const float n0 = kab_blank_sel(t0, th1a, th3, w, 1u << (sh + 0), 2u << (sh + 0), one);
+        const float m1 = kab_label_sel(a0, a1, a2, a3, w, 1u << (sh + 2), 2u << (sh + 2), one);
+        const float m2 = kab_blank_sel(t2, t1, th1b, w, 1u << (sh + 4), 2u << (sh + 4), one);
+        const float m3 = kab_label_sel(b0, b1, b2, b3, w, 1u << (sh + 6), 2u << (sh + 6), one);
         s0 = n0; s1 = m1; s2 = m2; s3 = m3;
       };
 
       int fic = 0;  // frame offset of the current group inside its emission chunk
       int lo_prev = 0;            // lo of the first frame of the previous group (<= lo of every later frame)
-      uint32_t drained = msg0;    // messages (global index) whose full-barrier phase this warp has observed
+      // neighbour FIFO in global memory: my inbox (messages of warp pgw) and the inbox of warp ngw
+      unsigned char *gws = p.fifo + (size_t)lat.scr_off * 4;
+      unsigned int *cons = reinterpret_cast<unsigned int *>(gws);
+      unsigned char *gfifo = gws + kab_bandp_fifo_off(NWT);
+      const unsigned char *inbox = gfifo + (size_t)gw * D * KAB_BP_MSG_BYTES + (lane < GH ? lane : 0) * 32;
+      unsigned char *outbox = gfifo + (size_t)ngw * D * KAB_BP_MSG_BYTES + (lane >= 32 - GH ? lane - (32 - GH) : 0) * 32;
+      uint32_t cons_seen = 0;      // messages the warp above is known to be done with
+      bool was_needed = false;     // the previous group read its message (the warp is inside the chain)
+      uint2 pf0 = make_uint2(0, 0), pf1 = pf0, pf2 = pf0, pf3 = pf0;  // message g-1, loaded a group early
 #ifdef KAB_BANDP_TIMING
       long long tm_ghost = 0, tm_emis = 0, tm_comp = 0, tm_pub = 0, tm_rel = 0, tm_bp = 0, tm_guard = 0, n_need = 0, n_safe = 0, tm_wait = 0, n_first = 0, tm_slow = 0;
       const long long tm_start = clock64();
@@ -367,20 +408,6 @@ __global__ void __launch_bounds__(KAB_BP_THREADS, 1)
         // one warp boundary of the ring is always in that situation, so the ring is a chain whose
         // head never waits and the others find their messages already delivered.
         if (g > 0) {
-          const uint32_t M = msg0 + (uint32_t)(g - 1), j = M % D;
-          // Phases complete in order, and a slot is returned to the producer only AFTER its message
-          // was seen to land (the producer arms the slot's next phase when it holds that credit):
-          // observe messages drained..last and return their slots.
-          auto catch_up = [&](const uint32_t last, const uint32_t credit_upto) {
-            for (uint32_t m = drained; m <= last; ++m) {
-              const uint32_t fbm = my_fifo + (uint32_t)KAB_BP_FULL_OFF + 8u * (m % D), par = (m / D) & 1u;
-              while (!kab_mbar_try_wait_addr(fbm, par)) {
-              }
-              if (lane == 0 && m < credit_upto)
-                kab_mbar_arrive_remote_relaxed(prv_fifo + (uint32_t)KAB_BP_EMPTY_OFF + 8u * (m % D));
-            }
-            if (drained <= last) drained = last + 1u;
-          };
           int qn2 = qg + qdg;
           if (rg + rdg >= T) ++qn2;
           const int hi1g = min(max(0, qn2 - half) + W, S);  // >= hi of every frame of this group
@@ -391,21 +418,40 @@ __global__ void __launch_bounds__(KAB_BP_THREADS, 1)
           const long long tw0 = clock64();
 #endif
           if (need) {
-            catch_up(M, M);
             if (!owned) {
-              const float4 x = *reinterpret_cast<const float4 *>(my_blk + (j * GH + lane) * 16);
-              s0 = x.x; s1 = x.y; s2 = x.z; s3 = x.w;
+              if (!was_needed) {  // (re)joining the chain: let the warp below get KAB_BP_LAG groups ahead
+                const int mt = min(g - 1 + KAB_BP_LAG - 1, n_groups - 2);
+                const unsigned char *ls = inbox + (size_t)(mt % D) * KAB_BP_MSG_BYTES;
+                while (kab_ld_volatile_b64(ls + 24).y != (uint32_t)(mt + 1)) __nanosleep(64);
+              }
+              const unsigned char *slot = inbox + (size_t)((g - 1) % D) * KAB_BP_MSG_BYTES;
+              const uint32_t seq = (uint32_t)g;
+              while (pf0.y != seq || pf1.y != seq || pf2.y != seq || pf3.y != seq) {
+                pf0 = kab_ld_volatile_b64(slot);
+                pf1 = kab_ld_volatile_b64(slot + 8);
+                pf2 = kab_ld_volatile_b64(slot + 16);
+                pf3 = kab_ld_volatile_b64(slot + 24);
+              }
+              s0 = __uint_as_float(pf0.x); s1 = __uint_as_float(pf1.x);
+              s2 = __uint_as_float(pf2.x); s3 = __uint_as_float(pf3.x);
             }
-            __syncwarp();
-            if (lane == 0) kab_mbar_arrive_remote_relaxed(prv_fifo + (uint32_t)KAB_BP_EMPTY_OFF + 8u * j);
-          } else {
-            if (!owned) { s0 = ninf; s1 = ninf; s2 = ninf; s3 = ninf; }
-            // keep the credits flowing: the producer may not be more than D/2 messages behind
-            if (M >= D / 2 && drained + D / 2 <= M) catch_up(M - D / 2, M);
+          } else if (!owned) {
+            s0 = ninf; s1 = ninf; s2 = ninf; s3 = ninf;
           }
+          was_needed = need;
+          __syncwarp();
+          if (lane == 0) kab_st_volatile_u32(&cons[gw], (uint32_t)g);  // done with messages 0 .. g-1
 #ifdef KAB_BANDP_TIMING
           tm_wait += clock64() - tw0;
 #endif
+        }
+        // message g (for the next group) may already be there: load it now, check it then
+        if (more && !owned) {
+          const unsigned char *slot = inbox + (size_t)(g % D) * KAB_BP_MSG_BYTES;
+          pf0 = kab_ld_volatile_b64(slot);
+          pf1 = kab_ld_volatile_b64(slot + 8);
+          pf2 = kab_ld_volatile_b64(slot + 16);
+          pf3 = kab_ld_volatile_b64(slot + 24);
         }
         lo_prev = max(0, qg - half);
         KAB_TM(tb);
@@ -438,16 +484,32 @@ __global__ void __launch_bounds__(KAB_BP_THREADS, 1)
 #endif
         if (safe) {
 #pragma unroll
-          for (int f = 0; f < G; ++f) frame(KabFalse{}, eb[f], e1[f], e3[f], f < 4 ? wlo : whi, 8 * (f & 3));
-        } else if (nfr == G) {
+          for (int f = 0; f < G; ++f) frame(eb[f], eb[f], e1[f], e3[f], f < 4 ? wlo : whi, 8 * (f & 3));
+        } else {
+          // edge warp (or the last, partial group): the exact per-frame window (S*i = q*T + r, no
+          // divisions) turned into masked emissions for the whole group
           q = qg; r = rg;
+          float mb0[G], mb2[G], mm1[G], mm3[G];
 #pragma unroll
-          for (int f = 0; f < G; ++f) frame(KabTrue{}, eb[f], e1[f], e3[f], f < 4 ? wlo : whi, 8 * (f & 3));
-        } else {  // the last, partial group of the lattice
-          q = qg; r = rg;
+          for (int f = 0; f < G; ++f) {
+            const int lo = max(0, q - half);   // align.py:64
+            const int hi = min(lo + W, S);     // align.py:65
+            q += qd; r += rd;
+            if (r >= T) { r -= T; ++q; }
+            const unsigned a = (unsigned)(vb - lo), wd = (unsigned)(hi - lo);
+            mb0[f] = (a + 0u < wd) ? eb[f] : ninf;
+            mm1[f] = (a + 1u < wd) ? e1[f] : ninf;
+            mb2[f] = (a + 2u < wd) ? eb[f] : ninf;
+            mm3[f] = (a + 3u < wd) ? e3[f] : ninf;
+          }
+          if (nfr == G) {
 #pragma unroll
-          for (int f = 0; f < G; ++f)
-            if (f < nfr) frame(KabTrue{}, eb[f], e1[f], e3[f], f < 4 ? wlo : whi, 8 * (f & 3));
+            for (int f = 0; f < G; ++f) frame(mb0[f], mb2[f], mm1[f], mm3[f], f < 4 ? wlo : whi, 8 * (f & 3));
+          } else {
+#pragma unroll
+            for (int f = 0; f < G; ++f)
+              if (f < nfr) frame(mb0[f], mb2[f], mm1[f], mm3[f], f < 4 ? wlo : whi, 8 * (f & 3));
+          }
         }
         qg = qn; rg = rn;
         KAB_TM(td);
@@ -458,16 +520,19 @@ __global__ void __launch_bounds__(KAB_BP_THREADS, 1)
 
         // ---- hand the top six lanes to the warp above (message g)
         if (more) {
-          const uint32_t M = msg0 + (uint32_t)g, j = M % D;
-          if (M >= D) {  // the consumer has returned slot j (it arrived on my empty barrier)
-            const uint32_t eb_addr = my_fifo + (uint32_t)KAB_BP_EMPTY_OFF + 8u * j, par = ((M / D) - 1u) & 1u;
-            while (!kab_mbar_try_wait_addr(eb_addr, par)) {
-            }
+          if (g >= D && (uint32_t)(g - D) >= cons_seen) {  // about to lap the consumer: read its progress
+            do {
+              cons_seen = kab_ld_volatile_u32(&cons[ngw]);
+            } while ((uint32_t)(g - D) >= cons_seen);
           }
-          if (lane == 32 - GH) kab_mbar_expect_tx_remote(nxt_fifo + (uint32_t)KAB_BP_FULL_OFF + 8u * j, GH * 16);
-          if (lane >= 32 - GH)
-            kab_st_async_v4(nxt_fifo + (j * GH + (uint32_t)(lane - (32 - GH))) * 16u, nxt_fifo + (uint32_t)KAB_BP_FULL_OFF + 8u * j, s0, s1, s2,
-                            s3);
+          if (lane >= 32 - GH) {
+            unsigned char *slot = outbox + (size_t)(g % D) * KAB_BP_MSG_BYTES;
+            const uint32_t seq = (uint32_t)(g + 1);
+            kab_st_volatile_b64(slot, __float_as_uint(s0), seq);
+            kab_st_volatile_b64(slot + 8, __float_as_uint(s1), seq);
+            kab_st_volatile_b64(slot + 16, __float_as_uint(s2), seq);
+            kab_st_volatile_b64(slot + 24, __float_as_uint(s3), seq);
+          }
         }
         KAB_TM(te);
         KAB_TM_ADD(tm_pub, td, te);
@@ -509,14 +574,6 @@ __global__ void __launch_bounds__(KAB_BP_THREADS, 1)
         d[6] = clock64() - tm_start; d[7] = n_groups; d[8] = tm_guard; d[9] = n_need; d[10] = n_safe; d[11] = tm_wait; d[12] = n_first; d[13] = tm_slow;
       }
 #endif
-      // every message of this lattice has landed (and its slot was returned) before the next lattice
-      for (uint32_t m = drained; m < msg0 + (uint32_t)(n_groups - 1); ++m) {
-        const uint32_t fbm = my_fifo + (uint32_t)KAB_BP_FULL_OFF + 8u * (m % D), par = (m / D) & 1u;
-        while (!kab_mbar_try_wait_addr(fbm, par)) {
-        }
-        if (lane == 0) kab_mbar_arrive_remote_relaxed(prv_fifo + (uint32_t)KAB_BP_EMPTY_OFF + 8u * (m % D));
-      }
-      drained = msg0 + (uint32_t)(n_groups - 1);
       // ---- end of the forward pass: cluster-wide forced end state (align.py:99-101)
       int cand = -1;
       if (owned) {
@@ -533,7 +590,6 @@ __global__ void __launch_bounds__(KAB_BP_THREADS, 1)
       }
     }
     echunks = ec0 + (uint32_t)n_chunks;
-    msgs = msg0 + (uint32_t)(n_groups - 1);
     __syncwarp();
     kab_cluster_sync();
 
@@ -616,40 +672,41 @@ __global__ void __launch_bounds__(KAB_BP_THREADS, 1)
             int *pbuf = pathbuf + buf * FBK;
             const unsigned char *rows = btbuf + ((size_t)buf * NREG + jreg) * RSZ;
             int col = (slot - base) >> 2, k2 = 2 * (slot & 3);  // byte column of the walker, bit offset in it
+            // Full groups are walked from registers (kab_walk_group8: two 64-bit loads per group, off
+            // the dependent chain); the frames it leaves (a second column step inside a group, a
+            // partial group) take the generic step below, which also handles the step into the
+            // warp region below (every ~370 frames).
+            auto step_column = [&]() {  // the walker's byte column drops by one
+              if (--col < 0) {          // ... into the region below (a move crosses at most one boundary)
+                wreg = wreg == 0 ? NWT - 1 : wreg - 1;
+                base = wreg * OW;
+                if (++jreg == NREG) restage();
+                rows = btbuf + ((size_t)buf * NREG + jreg) * RSZ;
+                col = (OW >> 2) - 1;
+              }
+            };
             for (int gq = (i1 - 1 - i0) >> 3; gq >= 0; --gq) {
-              // 64-bit words (8 frames) of the walker's byte column and of the column below it
-              const unsigned char *grow = rows + gq * 256;
-              uint2 wv = *reinterpret_cast<const uint2 *>(grow + col * 8);
-              uint2 wl = *reinterpret_cast<const uint2 *>(grow + max(col - 1, 0) * 8);
-              const int ftop = min(7, i1 - 1 - i0 - gq * 8);
+              int f = min(7, i1 - 1 - i0 - gq * 8);
               int *pg = pbuf + gq * 8;
-              unsigned long long w64 = ((unsigned long long)wv.y << 32) | wv.x;
-              // a ROLLED loop: the rare column change sits in the body once, and the common path is a
-              // dozen instructions that stay in the instruction cache
-#pragma unroll 1
-              for (int sh = 8 * ftop + k2; sh >= 0; sh -= 8) {
-                const int mv = (int)((w64 >> sh) & 3ull);
-                pg[sh >> 3] = v;
+              if (f == 7) {
+                const unsigned char *grow = rows + gq * 256;
+                const uint2 w0 = *reinterpret_cast<const uint2 *>(grow + col * 8);
+                const bool have1 = col > 0 || jreg + 1 < NREG;
+                const unsigned char *below = col > 0 ? grow + (col - 1) * 8 : grow + RSZ + ((OW >> 2) - 1) * 8;
+                const uint2 w1 = have1 ? *reinterpret_cast<const uint2 *>(below) : make_uint2(0u, 0u);
+                int nchg;
+                f = kab_walk_group8(w0, w1, have1, v, k2, pg, nchg);
+                for (int c = 0; c < nchg; ++c) step_column();
+              }
+              for (; f >= 0; --f) {  // generic step
+                const unsigned int byte = rows[gq * 256 + col * 8 + f];
+                pg[f] = v;
+                const int mv = (int)((byte >> k2) & 3u);
                 v -= mv;
-                sh -= 2 * mv;
                 k2 -= 2 * mv;
-                if (k2 < 0) {  // left the byte column (rare: every ~14 frames)
+                if (k2 < 0) {
                   k2 += 8;
-                  sh += 8;
-                  if (col == 0) {  // into the region below (a move crosses at most one boundary)
-                    wreg = wreg == 0 ? NWT - 1 : wreg - 1;
-                    base = wreg * OW;
-                    if (++jreg == NREG) restage();
-                    rows = btbuf + ((size_t)buf * NREG + jreg) * RSZ;
-                    grow = rows + gq * 256;
-                    col = (OW >> 2) - 1;
-                    wv = *reinterpret_cast<const uint2 *>(grow + col * 8);
-                  } else {
-                    --col;
-                    wv = wl;
-                  }
-                  w64 = ((unsigned long long)wv.y << 32) | wv.x;
-                  wl = *reinterpret_cast<const uint2 *>(grow + max(col - 1, 0) * 8);
+                  step_column();
                 }
               }
             }

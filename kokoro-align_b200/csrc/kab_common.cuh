@@ -31,6 +31,7 @@ struct KabParams {
   const int32_t *raw;       // raw label values (generic kernel: value-based blank test)
   uint8_t *bp;              // backpointer workspace
   float *scratch;           // generic kernel score rows
+  unsigned char *fifo;      // cluster band kernel: per-lattice progress counters and neighbour FIFOs
   int32_t *best_path;       // [sum T]
   int32_t *best_labels;     // [sum T]
   float *best_scores;       // [sum T]
@@ -149,6 +150,18 @@ __device__ __forceinline__ void kab_add2(float lo, float hi, float e, float &olo
       "}"
       : "=f"(olo), "=f"(ohi)
       : "f"(lo), "f"(hi), "f"(e));
+}
+// Packed add with two different addends: olo = lo + elo, ohi = hi + ehi (two IEEE-rn fp32 adds).
+__device__ __forceinline__ void kab_add2v(float lo, float hi, float elo, float ehi, float &olo, float &ohi) {
+  asm("{\n\t"
+      ".reg .b64 u, v, w;\n\t"
+      "mov.b64 u, {%2, %3};\n\t"
+      "mov.b64 v, {%4, %5};\n\t"
+      "add.rn.f32x2 w, u, v;\n\t"
+      "mov.b64 {%0, %1}, w;\n\t"
+      "}"
+      : "=f"(olo), "=f"(ohi)
+      : "f"(lo), "f"(hi), "f"(elo), "f"(ehi));
 }
 // Blank state: candidates a0 (move 0), a1 (move 1), a3 (move 3); ascending strict-'>' scan.
 // The predicated "OR" is issued as mad.lo (w = one * bit + w, `one` is a register holding 1 that

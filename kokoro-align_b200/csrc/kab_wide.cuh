@@ -74,23 +74,6 @@ __host__ __device__ inline KabWideGeom kab_wide_geom(int stage_bytes) {
   return g;
 }
 
-__device__ __forceinline__ void kab_st_volatile_b64(void *p, uint32_t lo, uint32_t hi) {
-  asm volatile("st.relaxed.gpu.global.v2.b32 [%0], {%1, %2};" ::"l"(p), "r"(lo), "r"(hi) : "memory");
-}
-__device__ __forceinline__ uint2 kab_ld_volatile_b64(const void *p) {
-  uint2 v;
-  asm volatile("ld.relaxed.gpu.global.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ uint32_t kab_ld_volatile_u32(const void *p) {
-  uint32_t v;
-  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void kab_st_volatile_u32(void *p, uint32_t v) {
-  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
 // Grid: n_fwd forward CTAs + 1 backtrack CTA (the last one), all resident.  Every CTA runs over the
 // wide lattices in the same order.
 __global__ void __launch_bounds__(KAB_WD_THREADS, 1)
@@ -479,24 +462,28 @@ __global__ void __launch_bounds__(KAB_WD_THREADS, 1)
           int *pbuf = pathbuf + buf * FBK;
           const unsigned char *rows = btbuf + ((size_t)buf * NREG + jreg) * RSZ;
           int col = (v - wreg * OW) >> 2, k2 = 2 * (v & 3);  // byte column of the walker, bit offset in it
-          // one byte load per frame: the shortest dependent chain (62 cycles per frame measured in
-          // kab_band.cuh; extracting from 64-bit words in registers was slower)
-          for (int il = i1 - 1 - i0; il >= 0; --il) {
-            const unsigned int byte = rows[(il >> 3) * 256 + col * 8 + (il & 7)];
-            pbuf[il] = v;
-            const int mv = (int)((byte >> k2) & 3u);
-            v -= mv;
-            k2 -= 2 * mv;
-            if (k2 < 0) {  // left the byte column
-              k2 += 8;
-              if (col == 0) {  // into the warp region below
-                --wreg;
-                if (++jreg == NREG) restage();
-                rows = btbuf + ((size_t)buf * NREG + jreg) * RSZ;
-                col = (OW >> 2) - 1;
-              } else {
-                --col;
+          // One byte load per frame.  The inner loop only knows the current warp region; the rare
+          // step into the region below (every ~370 frames) leaves it, so the common path stays a
+          // dozen instructions around the dependent chain LDS.U8 -> shift -> mask -> subtract.
+          int il = i1 - 1 - i0;
+          while (il >= 0) {
+            bool crossed = false;
+            for (; il >= 0; --il) {
+              const unsigned int byte = rows[(il >> 3) * 256 + col * 8 + (il & 7)];
+              pbuf[il] = v;
+              const int mv = (int)((byte >> k2) & 3u);
+              v -= mv;
+              k2 -= 2 * mv;
+              if (k2 < 0) {  // left the byte column
+                k2 += 8;
+                if (--col < 0) { crossed = true; --il; break; }
               }
+            }
+            if (crossed) {  // into the region below (a move crosses at most one boundary)
+              --wreg;
+              if (++jreg == NREG) restage();
+              rows = btbuf + ((size_t)buf * NREG + jreg) * RSZ;
+              col = (OW >> 2) - 1;
             }
           }
         } else if (tid >= 32 && b + 1 < n_blocks) {

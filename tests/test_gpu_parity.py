@@ -189,10 +189,11 @@ def test_random_shapes_and_beams(kab, seed):
     _compare_batch(kab, lp, t_off, labels, l_off, beam_size=W)
 
 
-@pytest.mark.parametrize("beam_size,cluster", [(1000, 1), (64, 1), (200, 2)])
-def test_cluster_band_kernel(kab, monkeypatch, beam_size, cluster):
-    """The opt-in pipelined cluster kernel (kab_bandp.cuh, KAB_BAND_CLUSTER) against the C oracle:
-    bit-exact like the default single-CTA band kernel."""
+@pytest.mark.parametrize("beam_size,cluster", [(1000, 1), (64, 1), (200, 2), (1000, 0), (64, 0), (300, 0)])
+def test_both_band_kernels(kab, monkeypatch, beam_size, cluster):
+    """The two band kernels against the C oracle, forced through KAB_BAND_CLUSTER: the pipelined
+    cluster kernel (kab_bandp.cuh, the default when every lattice gets its own cluster) and the
+    single-CTA kernel (kab_band.cuh, the default for larger batches, = 0 here)."""
     from kokoro_align_b200 import synth
     monkeypatch.setenv("KAB_BAND_CLUSTER", str(cluster))
     T = np.array([12000, 7001, 3000, 41, 5003])
