@@ -36,6 +36,17 @@ METRIC = "lattice cells/sec (TxS)"
 UNIT = "cells/s"
 
 
+def band_kernel_name(n_band, beam_size=1000):
+    """Which band kernel kab_plan_create picks (kab_api.cu): the pipelined cluster kernel when every
+    band lattice of the plan gets its own cluster of ceil(ceil((W + 32) / 104) / 4) CTAs at once."""
+    import torch
+    nc = -(-(-(-(beam_size + 32) // 104)) // 4)
+    sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    forced = os.environ.get("KAB_BAND_CLUSTER")
+    cluster = n_band <= sms // nc if forced is None else int(forced) >= 1
+    return "kab_bandp_kernel" if cluster else "kab_band_kernel"
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -300,7 +311,7 @@ def main():
             "gpu_launches": int(info.kernel_launches) * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "kab_warp_kernel" if info.n_class[0] >= info.n_class[1] else "kab_band_kernel",
+                         "kernel": "kab_warp_kernel" if info.n_class[0] >= info.n_class[1] else band_kernel_name(int(info.n_class[1])),
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kernel_ms},
             "cpu_baseline": cpu, "clocks": clocks,
         }
