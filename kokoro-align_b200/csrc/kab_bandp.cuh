@@ -685,15 +685,28 @@ __global__ void __launch_bounds__(KAB_BP_THREADS, 1)
                 col = (OW >> 2) - 1;
               }
             };
+            uint2 pw0 = make_uint2(0u, 0u), pw1 = pw0;  // words of the group below, loaded a group early
+            const unsigned char *pfrom = nullptr;       // ... from this column address (nullptr: nothing loaded)
             for (int gq = (i1 - 1 - i0) >> 3; gq >= 0; --gq) {
               int f = min(7, i1 - 1 - i0 - gq * 8);
               int *pg = pbuf + gq * 8;
               if (f == 7) {
                 const unsigned char *grow = rows + gq * 256;
-                const uint2 w0 = *reinterpret_cast<const uint2 *>(grow + col * 8);
                 const bool have1 = col > 0 || jreg + 1 < NREG;
-                const unsigned char *below = col > 0 ? grow + (col - 1) * 8 : grow + RSZ + ((OW >> 2) - 1) * 8;
-                const uint2 w1 = have1 ? *reinterpret_cast<const uint2 *>(below) : make_uint2(0u, 0u);
+                const unsigned char *c0 = grow + col * 8;
+                const unsigned char *below = col > 0 ? c0 - 8 : grow + RSZ + ((OW >> 2) - 1) * 8;
+                uint2 w0, w1;
+                if (pfrom == c0) {
+                  w0 = pw0; w1 = pw1;
+                } else {
+                  w0 = *reinterpret_cast<const uint2 *>(c0);
+                  w1 = have1 ? *reinterpret_cast<const uint2 *>(below) : make_uint2(0u, 0u);
+                }
+                if (gq > 0) {  // same column one group down: right unless the walk changes column now
+                  pw0 = *reinterpret_cast<const uint2 *>(c0 - 256);
+                  pw1 = have1 ? *reinterpret_cast<const uint2 *>(below - 256) : make_uint2(0u, 0u);
+                  pfrom = c0 - 256;
+                }
                 int nchg;
                 f = kab_walk_group8(w0, w1, have1, v, k2, pg, nchg);
                 for (int c = 0; c < nchg; ++c) step_column();

@@ -462,28 +462,53 @@ __global__ void __launch_bounds__(KAB_WD_THREADS, 1)
           int *pbuf = pathbuf + buf * FBK;
           const unsigned char *rows = btbuf + ((size_t)buf * NREG + jreg) * RSZ;
           int col = (v - wreg * OW) >> 2, k2 = 2 * (v & 3);  // byte column of the walker, bit offset in it
-          // One byte load per frame.  The inner loop only knows the current warp region; the rare
-          // step into the region below (every ~370 frames) leaves it, so the common path stays a
-          // dozen instructions around the dependent chain LDS.U8 -> shift -> mask -> subtract.
-          int il = i1 - 1 - i0;
-          while (il >= 0) {
-            bool crossed = false;
-            for (; il >= 0; --il) {
-              const unsigned int byte = rows[(il >> 3) * 256 + col * 8 + (il & 7)];
-              pbuf[il] = v;
-              const int mv = (int)((byte >> k2) & 3u);
-              v -= mv;
-              k2 -= 2 * mv;
-              if (k2 < 0) {  // left the byte column
-                k2 += 8;
-                if (--col < 0) { crossed = true; --il; break; }
-              }
-            }
-            if (crossed) {  // into the region below (a move crosses at most one boundary)
+          // Full groups are walked from registers (kab_walk_group8 in kab_bandp.cuh: two 64-bit loads
+          // per group, loaded a group early, and a branch-free 8-frame body); what it leaves takes the
+          // generic step, which also handles the step into the warp region below.
+          auto step_column = [&]() {
+            if (--col < 0) {
               --wreg;
               if (++jreg == NREG) restage();
               rows = btbuf + ((size_t)buf * NREG + jreg) * RSZ;
               col = (OW >> 2) - 1;
+            }
+          };
+          uint2 pw0 = make_uint2(0u, 0u), pw1 = pw0;
+          const unsigned char *pfrom = nullptr;
+          for (int gq = (i1 - 1 - i0) >> 3; gq >= 0; --gq) {
+            int f = min(7, i1 - 1 - i0 - gq * 8);
+            int *pg = pbuf + gq * 8;
+            if (f == 7) {
+              const unsigned char *grow = rows + gq * 256;
+              const bool have1 = col > 0 || (jreg + 1 < NREG && wreg > 0);
+              const unsigned char *c0 = grow + col * 8;
+              const unsigned char *below = col > 0 ? c0 - 8 : grow + RSZ + ((OW >> 2) - 1) * 8;
+              uint2 w0, w1;
+              if (pfrom == c0) {
+                w0 = pw0; w1 = pw1;
+              } else {
+                w0 = *reinterpret_cast<const uint2 *>(c0);
+                w1 = have1 ? *reinterpret_cast<const uint2 *>(below) : make_uint2(0u, 0u);
+              }
+              if (gq > 0) {
+                pw0 = *reinterpret_cast<const uint2 *>(c0 - 256);
+                pw1 = have1 ? *reinterpret_cast<const uint2 *>(below - 256) : make_uint2(0u, 0u);
+                pfrom = c0 - 256;
+              }
+              int nchg;
+              f = kab_walk_group8(w0, w1, have1, v, k2, pg, nchg);
+              for (int c = 0; c < nchg; ++c) step_column();
+            }
+            for (; f >= 0; --f) {  // generic step
+              const unsigned int byte = rows[gq * 256 + col * 8 + f];
+              pg[f] = v;
+              const int mv = (int)((byte >> k2) & 3u);
+              v -= mv;
+              k2 -= 2 * mv;
+              if (k2 < 0) {
+                k2 += 8;
+                step_column();
+              }
             }
           }
         } else if (tid >= 32 && b + 1 < n_blocks) {
