@@ -82,20 +82,8 @@ __device__ __forceinline__ uint32_t kab_mapa(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
-__device__ __forceinline__ void kab_st_cluster_v4(uint32_t addr, float a, float b, float c, float d) {
-  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
-               : "memory");
-}
 __device__ __forceinline__ void kab_st_cluster_u32(uint32_t addr, uint32_t v) {
   asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
-}
-__device__ __forceinline__ void kab_st_release_cluster_u32(uint32_t addr, uint32_t v) {
-  asm volatile("st.release.cluster.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t kab_ld_acquire_cluster_u32(uint32_t addr) {  // shared::cta address
-  uint32_t v;
-  asm volatile("ld.acquire.cluster.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-  return v;
 }
 __device__ __forceinline__ void kab_red_max_cluster_s32(uint32_t addr, int v) {
   asm volatile("red.relaxed.cluster.shared::cluster.max.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
@@ -105,22 +93,6 @@ __device__ __forceinline__ void kab_red_or_cluster_u32(uint32_t addr, uint32_t v
 }
 __device__ __forceinline__ void kab_mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(kab_smem_u32(bar)) : "memory");
-}
-// 16-byte store into (possibly remote) shared memory that completes 16 bytes on the mbarrier `bar`
-// of the same CTA: ordered by the hardware, no fence needed on either side
-__device__ __forceinline__ void kab_st_async_v4(uint32_t addr, uint32_t bar, float a, float b, float c, float d) {
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(
-                   addr),
-               "f"(a), "f"(b), "f"(c), "f"(d), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void kab_mbar_arrive_remote_relaxed(uint32_t bar) {  // shared::cluster address
-  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-// one arrival + `bytes` expected on a (possibly remote) mbarrier: the PRODUCER arms the consumer's slot
-__device__ __forceinline__ void kab_mbar_expect_tx_remote(uint32_t bar, uint32_t bytes) {  // shared::cluster address
-  asm volatile("mbarrier.arrive.expect_tx.relaxed.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
-               : "memory");
 }
 __device__ __forceinline__ bool kab_mbar_try_wait_addr(uint32_t bar, uint32_t parity) {
   uint32_t ok;
