@@ -96,6 +96,20 @@ def test_nonfinite_rejected(kab):
     lp[99, 38] = np.nan
     with pytest.raises(ValueError):
         kab.ctc_best_path(lp, labels, max_move=3)
+    # the wide (unbanded) kernel and the single-CTA band kernel check too
+    lp, labels = synth.make_lattice(900, 2000, seed=7)
+    lp[899, 0] = np.inf
+    with pytest.raises(ValueError):
+        kab.ctc_best_path(lp, labels, beam_size=9000)
+    import os
+    os.environ["KAB_BAND_CLUSTER"] = "0"
+    try:
+        lp, labels = synth.make_lattice(3000, 900, seed=8)
+        lp[17, 3] = -np.inf
+        with pytest.raises(ValueError):
+            kab.ctc_best_path(lp, labels)
+    finally:
+        del os.environ["KAB_BAND_CLUSTER"]
 
 
 def test_device_resident_torch(kab):
