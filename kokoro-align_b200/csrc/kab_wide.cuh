@@ -45,7 +45,9 @@
 #ifndef KAB_WD_LAG
 #define KAB_WD_LAG 2     // a warp starts once its lower neighbour has finished this many groups, so that
 #endif                   // every later message is already there when it is prefetched (a group early)
-#define KAB_WD_FBW 64    // frames per per-warp backpointer block
+#ifndef KAB_WD_FBW
+#define KAB_WD_FBW 128   // frames per per-warp backpointer block (256 would cost the second resident CTA per SM)
+#endif
 #define KAB_WD_FBK 128   // frames per backtrack block
 #define KAB_WD_NREG 3    // warp regions staged per backtrack block
 #define KAB_WD_THREADS ((KAB_WD_CW + 1) * 32)
