@@ -16,6 +16,7 @@
 #include "kab_bandp.cuh"
 #include "kab_wide.cuh"
 #include "kab_common.cuh"
+#include "kab_compact.cuh"
 #include "kab_generic.cuh"
 #include "kab_warp.cuh"
 
@@ -61,6 +62,10 @@ struct kab_plan {
   int device = 0;
   int64_t B = 0, total_T = 0, total_L = 0;
   int32_t V = 0, W = 0, M = 0;
+  int32_t Vc = 0;              // > 0: the staged kernels work on compact log-probs of Vc columns (kab_compact.cuh)
+  int32_t *d_gather = nullptr;  // [B][Vc] compact column -> column of log_probs (= label value)
+  float *d_lpc = nullptr;       // [sum T][Vc] compact log-probs
+  int max_T[4] = {0, 0, 0, 0};  // longest lattice of every work list (grid of the compaction kernels)
   int sm_count = 0;
   int32_t stage_frames = 0, stage_bytes = 0;
   int32_t band_nw = 0;  // warps per CTA of the band kernel (ring of 104 * band_nw states)
@@ -107,7 +112,7 @@ int plan_free(kab_plan *pl) {
   cudaSetDevice(pl->device);
   for (int q = 0; q < N_QUEUES; ++q) cudaFree(pl->d_lists[q]);
   cudaFree(pl->d_col16); cudaFree(pl->d_raw); cudaFree(pl->d_bp); cudaFree(pl->d_scratch);
-  cudaFree(pl->d_queue); cudaFree(pl->d_status_init); cudaFree(pl->d_wide_ws); cudaFree(pl->d_band_fifo);
+  cudaFree(pl->d_queue); cudaFree(pl->d_status_init); cudaFree(pl->d_wide_ws); cudaFree(pl->d_band_fifo); cudaFree(pl->d_gather); cudaFree(pl->d_lpc);
   cudaFree(pl->d_lp); cudaFree(pl->d_path); cudaFree(pl->d_lab); cudaFree(pl->d_st);
   cudaFree(pl->d_sc); cudaFree(pl->d_fs);
   if (pl->stream) cudaStreamDestroy(pl->stream);
@@ -170,13 +175,40 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
   if (ce != cudaSuccess) { delete pl; return cuda_fail(ce, "cudaGetDeviceProperties"); }
   pl->sm_count = prop.multiProcessorCount;
 
+  // ---- wide vocabularies: can the staged kernels work on a compact copy of the log-probs?
+  // (every lattice they would take uses at most MAX_STAGE_V - 1 distinct label columns)
+  std::vector<int32_t> h_gather;
+  if (V > MAX_STAGE_V && M == 4) {
+    std::vector<uint8_t> seen((size_t)V, 0);
+    int64_t dmax = 0;
+    bool any = false;
+    for (int64_t b = 0; b < B; ++b) {
+      const int64_t L = l_off[b + 1] - l_off[b];
+      const int32_t *lab = labels + l_off[b];
+      bool usable = true;
+      int64_t dist = 0;
+      for (int64_t l = 0; l < L && usable; ++l) {
+        if (lab[l] <= 0 || lab[l] >= V) usable = false;
+        else if (!seen[(size_t)lab[l]]) { seen[(size_t)lab[l]] = 1; ++dist; }
+      }
+      for (int64_t l = 0; l < L; ++l)
+        if (lab[l] > 0 && lab[l] < V) seen[(size_t)lab[l]] = 0;
+      if (usable) { dmax = std::max(dmax, dist); any = true; }
+    }
+    if (any && dmax + 1 <= MAX_STAGE_V) {
+      pl->Vc = (int32_t)std::max<int64_t>(8, align_up(dmax + 1, 4));
+      h_gather.assign((size_t)B * pl->Vc, 0);
+    }
+  }
+  const int32_t Veff = pl->Vc ? pl->Vc : V;  // vocabulary the staged kernels see
+
   // emission staging geometry: ~4 KB stages, at most 16 frames each
-  pl->stage_frames = V <= 64 ? 16 : 8;  // multiple of 8: frame groups never straddle stages
+  pl->stage_frames = Veff <= 64 ? 16 : 8;  // multiple of 8: frame groups never straddle stages
   if (const char *sf = getenv("KAB_STAGE_FRAMES")) {  // development knob: 8 or 16
     const int v = atoi(sf);
     if (v == 8 || v == 16 || v == 32) pl->stage_frames = v;
   }
-  pl->stage_bytes = (int32_t)align_up((int64_t)pl->stage_frames * V * 4 + 24, 16);
+  pl->stage_bytes = (int32_t)align_up((int64_t)pl->stage_frames * Veff * 4 + 24, 16);
 
   // resident CTAs of the wide kernel (its warps spin on each other: the whole grid must be resident)
   int wide_capacity = 0;
@@ -220,11 +252,21 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
     d.lab_off = l_off[b];
     d.T = (int32_t)T; d.L = (int32_t)L; d.index = (int32_t)b;
     d.col_off = (int64_t)col16.size();
-    for (int64_t l = 0; l < L; ++l) col16.push_back((uint16_t)(lab[l] < 0 ? lab[l] + V : lab[l]));
+    if (pl->Vc && !special) {
+      // compact numbering: blank 0, then the lattice's distinct label columns in ascending order
+      int32_t *g = h_gather.data() + (size_t)b * pl->Vc;
+      int32_t n = 1;
+      for (int w = 0; w < 1024; ++w)
+        for (int64_t m = distinct_mask[w]; m; m &= m - 1) g[n++] = w * 64 + __builtin_ctzll((unsigned long long)m);
+      for (int64_t l = 0; l < L; ++l)
+        col16.push_back((uint16_t)(std::lower_bound(g + 1, g + n, lab[l]) - g));
+    } else {
+      for (int64_t l = 0; l < L; ++l) col16.push_back((uint16_t)(lab[l] < 0 ? lab[l] + V : lab[l]));
+    }
     while (col16.size() % 8) col16.push_back(0);
     for (int k = 0; k < 8; ++k) col16.push_back(0);
 
-    const bool fast = M == 4 && !special && V <= MAX_STAGE_V;
+    const bool fast = M == 4 && !special && Veff <= MAX_STAGE_V;
     const bool full = W >= S && (S * (T - 1)) / T <= W / 2;
     const int64_t weff = std::min<int64_t>(W, S);
     int q;
@@ -254,6 +296,7 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
       scr_floats += align_up(2 * (S + 16), 64);
     }
     pl->lists[q].push_back(d);
+    pl->max_T[q] = std::max(pl->max_T[q], (int)T);
     info.n_class[q == Q_WARP ? KAB_CLASS_WARP : (q == Q_GENERIC ? KAB_CLASS_GENERIC : (q == Q_WIDE ? KAB_CLASS_WIDE : KAB_CLASS_BAND))]++;
     const int64_t cells = cells_eval_of(T, S, W);
     info.cells_eval += cells;
@@ -320,6 +363,11 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
       rc = up((void **)&pl->d_lists[q], pl->lists[q].data(), pl->lists[q].size() * sizeof(KabLattice));
     if (rc) break;
     if ((rc = up((void **)&pl->d_col16, col16.data(), col16.size() * sizeof(uint16_t)))) break;
+    if (pl->Vc) {
+      if ((rc = up((void **)&pl->d_gather, h_gather.data(), h_gather.size() * sizeof(int32_t)))) break;
+      cudaError_t e2 = cudaMalloc((void **)&pl->d_lpc, (size_t)pl->total_T * pl->Vc * sizeof(float));
+      if (e2 != cudaSuccess) { rc = cuda_fail(e2, "cudaMalloc(compact log-probs)"); break; }
+    }
     if (!pl->lists[Q_GENERIC].empty())
       if ((rc = up((void **)&pl->d_raw, labels, (size_t)pl->total_L * sizeof(int32_t)))) break;
     if (pl->any_bad_label)
@@ -332,7 +380,7 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
     // ---- launch geometry
     if (!pl->lists[Q_WARP].empty()) {
       const size_t smem = 128 + (size_t)KAB_WARPS_PER_CTA * (KAB_WARP_STAGES * pl->stage_bytes + 256);  // + label tables
-      const void *fn = V == 39 ? (const void *)kab_warp_kernel<39> : (const void *)kab_warp_kernel<0>;
+      const void *fn = Veff == 39 ? (const void *)kab_warp_kernel<39> : (const void *)kab_warp_kernel<0>;
       if ((e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) { rc = cuda_fail(e, "cudaFuncSetAttribute(warp)"); break; }
       int occ = 0;
       if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, KAB_WARPS_PER_CTA * 32, smem)) != cudaSuccess) { rc = cuda_fail(e, "occupancy(warp)"); break; }
@@ -417,13 +465,27 @@ int kab_plan_run_device(kab_plan *pl, const float *d_log_probs, int32_t *d_best_
   p.one = 1u;
   p.band_nw = pl->band_nw;
 
+  // the staged kernels' view of the log-probs: the caller's array, or its compact copy
+  KabParams pf = p;
+  const int fast_lists[3] = {Q_WARP, Q_BAND, Q_WIDE};
+  if (pl->Vc) {
+    for (int q : fast_lists)
+      if (!pl->lists[q].empty()) {
+        const dim3 grid((unsigned)pl->lists[q].size(), (unsigned)((pl->max_T[q] + KAB_COMPACT_FRAMES - 1) / KAB_COMPACT_FRAMES));
+        kab_compact_kernel<<<grid, 256, 0, stream>>>(pl->d_lists[q], d_log_probs, pl->d_lpc, pl->d_gather, pl->V, pl->Vc);
+      }
+    pf.lp = pl->d_lpc;
+    pf.V = pl->Vc;
+    pf.lp_bytes = pl->total_T * (int64_t)pl->Vc * 4;
+  }
+
   KAB_CUDA(cudaMemsetAsync(pl->d_queue, 0, N_QUEUES * sizeof(unsigned int), stream));
   if (pl->any_bad_label)
     KAB_CUDA(cudaMemcpyAsync(d_status, pl->d_status_init, (size_t)pl->B * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
 
   if (!pl->lists[Q_WARP].empty()) {
-    KabParams pw = p; pw.queue = pl->d_queue + Q_WARP;
-    if (pl->V == 39)
+    KabParams pw = pf; pw.queue = pl->d_queue + Q_WARP;
+    if (pf.V == 39)
       kab_warp_kernel<39><<<pl->grid[Q_WARP], KAB_WARPS_PER_CTA * 32, pl->smem[Q_WARP], stream>>>(
           pl->d_lists[Q_WARP], (int)pl->lists[Q_WARP].size(), pw);
     else
@@ -431,7 +493,7 @@ int kab_plan_run_device(kab_plan *pl, const float *d_log_probs, int32_t *d_best_
           pl->d_lists[Q_WARP], (int)pl->lists[Q_WARP].size(), pw);
   }
   if (!pl->lists[Q_BAND].empty()) {
-    KabParams pb = p; pb.queue = pl->d_queue + Q_BAND;
+    KabParams pb = pf; pb.queue = pl->d_queue + Q_BAND;
 #ifdef KAB_BAND_TIMING
     static long long *dbg = nullptr;
     if (!dbg) cudaMalloc((void **)&dbg, 32 * 8 * sizeof(long long));
@@ -497,7 +559,7 @@ int kab_plan_run_device(kab_plan *pl, const float *d_log_probs, int32_t *d_best_
     static long long *wdbg2 = nullptr;
     if (!wdbg2) cudaMalloc((void **)&wdbg2, 64 * sizeof(long long));
     cudaMemsetAsync(wdbg2, 0, 64 * sizeof(long long), stream);
-    p.debug = wdbg2;
+    pf.debug = wdbg2;
     struct WideDbgPrint {
       long long *d; cudaStream_t s;
       ~WideDbgPrint() {
@@ -519,10 +581,16 @@ int kab_plan_run_device(kab_plan *pl, const float *d_log_probs, int32_t *d_best_
     const KabLattice *wl = pl->d_lists[Q_WIDE];
     int wn = (int)pl->lists[Q_WIDE].size();
     unsigned char *wws = pl->d_wide_ws;
-    void *wargs[] = {(void *)&wl, (void *)&wn, (void *)&p, (void *)&wws};
+    void *wargs[] = {(void *)&wl, (void *)&wn, (void *)&pf, (void *)&wws};
     KAB_CUDA(cudaLaunchCooperativeKernel((const void *)kab_wide_kernel, dim3((unsigned)pl->grid[Q_WIDE]),
                                          dim3(KAB_WD_THREADS), wargs, pl->smem[Q_WIDE], stream));
   }
+  if (pl->Vc)  // best_labels of the staged kernels: compact index -> label value
+    for (int q : fast_lists)
+      if (!pl->lists[q].empty()) {
+        const dim3 grid((unsigned)pl->lists[q].size(), (unsigned)((pl->max_T[q] + KAB_COMPACT_FRAMES - 1) / KAB_COMPACT_FRAMES));
+        kab_expand_labels_kernel<<<grid, 64, 0, stream>>>(pl->d_lists[q], d_best_labels, d_status, pl->d_gather, pl->Vc);
+      }
   if (!pl->lists[Q_GENERIC].empty()) {
     KabParams pg = p; pg.queue = pl->d_queue + Q_GENERIC;
     kab_generic_kernel<GENERIC_NT><<<pl->grid[Q_GENERIC], GENERIC_NT, 0, stream>>>(

@@ -218,19 +218,29 @@ def test_both_band_kernels(kab, monkeypatch, beam_size, cluster):
     assert info.n_class[1] >= 4
 
 
-@pytest.mark.parametrize("V", [128, 256, 512, 600])
+@pytest.mark.parametrize("V", [128, 256, 512, 600, 4096])
 def test_wide_vocabularies(kab, V):
-    """Vocabularies up to 512 columns run in the staged warp / band kernels (whole rows staged),
-    wider ones in the generic kernel; all bit-exact against the C oracle."""
+    """Vocabularies up to 512 columns run in the staged kernels with whole rows staged; wider ones
+    (BASELINE config 5: V = 4096) on a compact copy of the columns the lattices use
+    (kab_compact.cuh); all bit-exact against the C oracle, best_labels in original label values."""
     from kokoro_align_b200 import synth
     T = np.array([700, 90, 3000, 431])
-    L = np.array([100, 12, 800, 60])
+    L = np.array([100, 12, 400, 60])
     lp, t_off, labels, l_off = synth.make_batch(T, L, V=V, seed=5100 + V, planted=True)
     info = _compare_batch(kab, lp, t_off, labels, l_off, beam_size=300, V=V)
-    if V <= 512:
-        assert info.n_class[0] == 2 and info.n_class[1] == 2
-    else:
-        assert info.n_class[2] == 4
+    assert info.n_class[0] == 2 and info.n_class[1] == 2 and info.n_class[2] == 0
+
+
+def test_wide_vocabulary_too_many_labels(kab):
+    """More than 511 distinct labels in one lattice: no compact copy, the generic kernel takes the
+    plan (still bit-exact)."""
+    from kokoro_align_b200 import synth
+    T = np.array([2500, 300])
+    L = np.array([900, 40])
+    lp, t_off, labels, l_off = synth.make_batch(T, L, V=4096, seed=5200)
+    assert len(np.unique(labels[:900])) > 511
+    info = _compare_batch(kab, lp, t_off, labels, l_off, V=4096)
+    assert info.n_class[2] == 2
 
 
 def test_config4_banded_million_frames(kab):
