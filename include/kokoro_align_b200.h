@@ -103,6 +103,26 @@ int kab_plan_run_host(kab_plan *plan, const float *h_log_probs, int32_t *h_best_
                       int32_t *h_status);
 
 /*
+ * align.py:116-117 on the device: rows of raw encoder logits ->
+ * log-probabilities, `x -= mean(x); x - log(sum(exp(x)))`, every fp32 operation and both row
+ * sums in numpy's order; exp / log are CUDA's expf / logf, so the result agrees with numpy's to
+ * a few ulp (4e-6 absolute in the tests), NOT bit for bit -- numpy's own SIMD exp is
+ * CPU-dependent.  d_log_probs may equal d_logits (in place).  Asynchronous on `stream`.
+ */
+int kab_log_softmax_device(const float *d_logits, float *d_log_probs, int64_t n_rows,
+                           int32_t vocab_size, void *stream);
+
+/*
+ * kab_plan_run_host for RAW LOGITS (the `*.logits.npz` rows of align.py:113-114): copies them to
+ * the device, normalises them there (kab_log_softmax_device, in place) and aligns.  Opt-in: the
+ * alignment is exact for the device's log-probs, which differ from numpy's by a few ulp.
+ * h_log_probs, if not NULL, receives the [sum T, V] log-probs the alignment used.
+ */
+int kab_plan_run_host_logits(kab_plan *plan, const float *h_logits, int32_t *h_best_path,
+                             int32_t *h_best_labels, float *h_best_scores, float *h_final_score,
+                             int32_t *h_status, float *h_log_probs);
+
+/*
  * One-shot single lattice with host buffers == kokoro_align/align.py:43
  * ctc_best_path(log_probs[T,V], labels[L], beam_size, max_move) -> (best_path, best_labels,
  * best_scores); *status receives KAB_ST_*; final_score may be NULL.

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 SO_PATH = os.path.join(_HERE, "libkokoro_align_b200.so")
 SOURCES = [os.path.join(_HERE, "csrc", f) for f in
-           ("kab_api.cu", "kab_common.cuh", "kab_warp.cuh", "kab_band.cuh", "kab_bandp.cuh", "kab_wide.cuh", "kab_compact.cuh", "kab_generic.cuh")]
+           ("kab_api.cu", "kab_common.cuh", "kab_warp.cuh", "kab_band.cuh", "kab_bandp.cuh", "kab_wide.cuh", "kab_compact.cuh", "kab_generic.cuh", "kab_softmax.cuh")]
 HEADER = os.path.join(_ROOT, "include", "kokoro_align_b200.h")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
@@ -22,7 +22,7 @@ ST_OK, ST_DEAD_BAND, ST_BAD_LABEL, ST_NONFINITE = 0, 1, 2, 3
 
 EXPORTS = ["kab_version", "kab_error_string", "kab_last_cuda_error", "kab_device_count",
            "kab_plan_create", "kab_plan_get_info", "kab_plan_destroy", "kab_plan_run_device",
-           "kab_plan_run_host", "kab_ctc_best_path", "kab_host_alloc", "kab_host_free"]
+           "kab_plan_run_host", "kab_plan_run_host_logits", "kab_log_softmax_device", "kab_ctc_best_path", "kab_host_alloc", "kab_host_free"]
 
 
 class PlanInfo(ctypes.Structure):
@@ -83,6 +83,8 @@ def lib():
     L.kab_plan_destroy.argtypes = [vp]
     L.kab_plan_run_device.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
     L.kab_plan_run_host.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    L.kab_plan_run_host_logits.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
+    L.kab_log_softmax_device.argtypes = [vp, vp, i64, i32, vp]
     L.kab_ctc_best_path.argtypes = [vp, i64, i32, vp, i64, i32, i32, vp, vp, vp, vp, vp]
     L.kab_host_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_size_t]
     L.kab_host_free.argtypes = [vp]

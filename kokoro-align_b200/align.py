@@ -73,7 +73,10 @@ class AlignPlan:
         self.close()
 
     # -- host buffers in, host buffers out (H2D + kernels + D2H inside the call)
-    def run_host(self, log_probs, out=None):
+    def run_host(self, log_probs, out=None, logits=False, log_probs_out=None):
+        """logits=True: ``log_probs`` holds RAW LOGITS and align.py:116-117 runs on the device
+        (kab_softmax.cuh; a few ulp from numpy's values, so opt-in); ``log_probs_out`` (float32
+        [sum T, V]) then receives the log-probs that were aligned."""
         lp = np.ascontiguousarray(log_probs, dtype=np.float32)
         if lp.shape != (self.total_T, self.V):
             raise ValueError(f"log_probs must have shape {(self.total_T, self.V)}, got {lp.shape}")
@@ -82,8 +85,16 @@ class AlignPlan:
                    np.empty(self.total_T, np.float32), np.empty(self.B, np.float32),
                    np.empty(self.B, np.int32))
         path, labs, scores, final, status = out
-        _lib.check(_lib.lib().kab_plan_run_host(self._h, _ptr(lp), _ptr(path), _ptr(labs),
-                                                _ptr(scores), _ptr(final), _ptr(status)))
+        if logits:
+            if log_probs_out is not None:
+                assert log_probs_out.dtype == np.float32 and log_probs_out.flags.c_contiguous \
+                    and log_probs_out.shape == lp.shape
+            _lib.check(_lib.lib().kab_plan_run_host_logits(self._h, _ptr(lp), _ptr(path), _ptr(labs),
+                                                           _ptr(scores), _ptr(final), _ptr(status),
+                                                           _ptr(log_probs_out)))
+        else:
+            _lib.check(_lib.lib().kab_plan_run_host(self._h, _ptr(lp), _ptr(path), _ptr(labs),
+                                                    _ptr(scores), _ptr(final), _ptr(status)))
         return path, labs, scores, final, status
 
     # -- device pointers (e.g. torch tensors' data_ptr()), asynchronous on `stream`
@@ -158,6 +169,22 @@ def log_softmax(logits):
     return logits - np.log(np.sum(np.exp(logits), axis=-1, keepdims=True))
 
 
+def log_softmax_torch(logits, out=None, stream=None):
+    """align.py:116-117 on the device: CUDA float32 tensor [rows, V] of raw logits -> log-probs
+    (``out`` may be ``logits`` itself: in place).  See kab_softmax.cuh for the parity statement."""
+    import torch
+    assert logits.is_cuda and logits.dtype == torch.float32 and logits.is_contiguous() and logits.dim() == 2
+    if out is None:
+        out = torch.empty_like(logits)
+    assert out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and out.shape == logits.shape
+    s = torch.cuda.current_stream(logits.device) if stream is None else stream
+    with torch.cuda.device(logits.device):
+        _lib.check(_lib.lib().kab_log_softmax_device(ctypes.c_void_p(logits.data_ptr()),
+                                                     ctypes.c_void_p(out.data_ptr()), logits.shape[0],
+                                                     logits.shape[1], ctypes.c_void_p(s.cuda_stream)))
+    return out
+
+
 def read_transcript_labels(voca_file):
     """Labels of a ``text|voca`` transcript: transcript.py:60-67 + encoder.py:5-19 (tokens
     outside the 39-symbol vocabulary are dropped, int8 ids)."""
@@ -170,30 +197,124 @@ def read_transcript_labels(voca_file):
     return encode_text(' '.join(res))
 
 
-def best_path(input_file, voca_file, output_file):
+def best_path(input_file, voca_file, output_file, device_log_softmax=False):
     """Drop-in for kokoro_align.align.best_path (align.py:112-124): raw logits npz + voca.txt
-    -> best_path.npz {best_path, best_labels, best_scores}."""
+    -> best_path.npz {best_path, best_labels, best_scores}.
+
+    device_log_softmax=True (opt-in) normalises the logits on the GPU
+    instead of in numpy: the log-probs then differ from numpy's by a few ulp (kab_softmax.cuh)."""
     with np.load(input_file) as f:
         logits = f['data']
-    log_probs = log_softmax(logits)
     labels = read_transcript_labels(voca_file)
-    path, labs, scores = ctc_best_path(log_probs, labels)
+    if device_log_softmax:
+        logits = np.ascontiguousarray(logits, dtype=np.float32)
+        T, V = logits.shape
+        if T == 0:
+            raise IndexError("list index out of range")
+        with AlignPlan([0, T], labels, [0, len(labels)], V, device=_current_device()) as plan:
+            path, labs, scores, _, status = plan.run_host(logits, logits=True)
+        raise_for_status(int(status[0]), V)
+    else:
+        path, labs, scores = ctc_best_path(log_softmax(logits), labels)
     np.savez(output_file, best_path=path, best_labels=labs, best_scores=scores)
 
 
-def best_path_files(logits_files, voca_files, best_path_files, skip_existing=True, beam_size=1000,
-                    max_move=4, verbose=True):
-    """The per-book loop of run_example.py:247-254 as ONE batch: every chapter whose output does
-    not exist yet is loaded, normalised (align.py:116-117), and all of them are aligned in a single
-    plan -- the chapters are independent lattices, so they run side by side on the GPU (36
-    chapters of a 9-hour book take the time of the longest one).  Writes the same best_path.npz
-    files, prints the reference's two messages, and raises the reference's exception for the first
-    chapter that fails (after the other chapters have been written).  Returns the written paths.
+# ----- npz wire format (SURVEY.md 8(f) rank 3): {data, indices} written by preprocess.py:12-35 /
+# train.py:228 with np.savez, i.e. a ZIP archive of STORED .npy members.  The rows of a stored
+# member are one contiguous byte range of the file, so they are read straight into (pinned)
+# batch memory -- no intermediate array, no concatenation.
 
-    Under torch.distributed (one process per GPU) the chapters are sharded over the ranks by
-    cost (parallel.align_sharded: no collective on the data path, a host-side gather of the
-    results) and rank 0 writes the files."""
+def npz_member_info(path, key='data'):
+    """(shape, dtype, byte offset of the array data or None when the member is compressed)."""
+    import struct
+    import zipfile
+    from numpy.lib import format as npf
+    with zipfile.ZipFile(path) as z:
+        zi = z.getinfo(key + '.npy')
+        with z.open(zi) as m:
+            version = npf.read_magic(m)
+            if version == (1, 0):
+                shape, fortran, dtype = npf.read_array_header_1_0(m)
+            else:
+                shape, fortran, dtype = npf.read_array_header_2_0(m)
+            header_len = m.tell()
+        if fortran and len(shape) > 1:
+            return shape, dtype, None
+        if zi.compress_type != zipfile.ZIP_STORED:
+            return shape, dtype, None
+        with open(path, 'rb') as f:
+            f.seek(zi.header_offset)
+            local = f.read(30)
+        if local[:4] != b'PK\x03\x04':
+            return shape, dtype, None
+        n_name, n_extra = struct.unpack('<HH', local[26:30])
+        return shape, dtype, zi.header_offset + 30 + n_name + n_extra + header_len
+
+
+def npz_read_into(path, dst, key='data', info=None):
+    """Read member ``key`` of an npz into the C-contiguous array ``dst`` (same shape and dtype):
+    one readinto() from the file for stored members, np.load otherwise."""
+    shape, dtype, offset = info or npz_member_info(path, key)
+    if tuple(shape) != dst.shape:
+        raise ValueError(f"{path}:{key} has shape {shape}, expected {dst.shape}")
+    if offset is None or dtype != dst.dtype:
+        with np.load(path) as f:
+            dst[...] = f[key]
+        return dst
+    view = memoryview(dst.reshape(-1).view(np.uint8))
+    with open(path, 'rb', buffering=0) as f:
+        f.seek(offset)
+        got = 0
+        while got < len(view):
+            n = f.readinto(view[got:])
+            if not n:
+                raise OSError(f"{path}: truncated member {key}")
+            got += n
+    return dst
+
+
+class _PinnedPool:
+    """One grow-only pinned host buffer per process (cudaHostAlloc is slow: ~0.2 ms / MB), reused
+    by consecutive best_path_files calls."""
+    ptr, size = None, 0
+
+    @classmethod
+    def array(cls, shape, dtype=np.float32):
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        if n > cls.size:
+            L = _lib.lib()
+            if cls.ptr:
+                _lib.check(L.kab_host_free(cls.ptr))
+                cls.ptr, cls.size = None, 0
+            p = ctypes.c_void_p(0)
+            want = max(n, 1 << 20)
+            _lib.check(L.kab_host_alloc(ctypes.byref(p), want))
+            cls.ptr, cls.size = p, want
+        buf = (ctypes.c_uint8 * max(n, 1)).from_address(cls.ptr.value)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+
+def best_path_files(logits_files, voca_files, best_path_files, skip_existing=True, beam_size=1000,
+                    max_move=4, verbose=True, device_log_softmax=False, io_threads=8, timings=None,
+                    align_fn=None):
+    """The per-book loop of run_example.py:247-254 as ONE batch: every chapter whose output does
+    not exist yet is read straight into one pinned batch buffer (npz_read_into), normalised
+    (align.py:116-117: numpy on the host by default -- bit-identical to the reference -- or on the
+    GPU with device_log_softmax=True), and all of them are aligned in a single plan: the chapters
+    are independent lattices, so they run side by side on the GPU (36 chapters of a 9-hour book
+    take the time of the longest one).  Writes the same best_path.npz files, prints the
+    reference's two messages, and raises the reference's exception for the first chapter that
+    fails (after the other chapters have been written).  Returns the written paths.
+
+    Under torch.distributed (one process per GPU) every rank reads and aligns its own LPT shard
+    of the chapters (parallel.shard_batch: no collective on the data path) and writes its own
+    output files; the written paths are gathered on rank 0 (other ranks return []).
+    ``timings``: optional dict that receives the wall seconds of every phase."""
     import os
+    import time
+    from concurrent.futures import ThreadPoolExecutor
+    from . import parallel
+    t_start = time.perf_counter()
     todo = []
     for lf, vf, bf in zip(logits_files, voca_files, best_path_files):
         if skip_existing and os.path.exists(bf):
@@ -203,26 +324,76 @@ def best_path_files(logits_files, voca_files, best_path_files, skip_existing=Tru
             todo.append((lf, vf, bf))
     if not todo:
         return []
-    lps, labs = [], []
-    for lf, vf, _ in todo:
-        with np.load(lf) as f:
-            lps.append(np.ascontiguousarray(log_softmax(f['data']), dtype=np.float32))
-        labs.append(np.asarray(read_transcript_labels(vf), dtype=np.int32))
-    from . import parallel
-    V = lps[0].shape[1]
-    results = parallel.align_sharded(lps, labs, beam_size=beam_size, max_move=max_move,
-                                     device=_current_device())
-    if results is None:  # not the gathering rank
-        return []
+    try:
+        import torch.distributed as dist
+        world = dist.get_world_size() if dist.is_initialized() else 1
+        rank = dist.get_rank() if dist.is_initialized() else 0
+    except ImportError:
+        world, rank = 1, 0
+    infos = [npz_member_info(lf) for lf, _, _ in todo]
+    labs = [np.asarray(read_transcript_labels(vf), dtype=np.int32) for _, vf, _ in todo]
+    for (shape, _, _), (lf, _, _) in zip(infos, todo):
+        if len(shape) != 2 or shape[1] != infos[0][0][1]:
+            raise ValueError(f"{lf}: logits must be [T, {infos[0][0][1]}], got {shape}")
+    V = int(infos[0][0][1])
+    T_all = [int(i[0][0]) for i in infos]
+    mine = [int(i) for i in parallel.shard_batch(T_all, [len(x) for x in labs], rank, world, beam_size)]
     written, first_bad = [], ST_OK
-    for (_, _, bf), (path, lab, sc, _, st) in zip(todo, results):
-        if st != ST_OK:
-            first_bad = first_bad or st
-            continue
-        if verbose:
-            print(f'Writing {bf}')
-        np.savez(bf, best_path=path, best_labels=lab, best_scores=sc)
-        written.append(bf)
+    t_read = t_norm = t_align = t_write = 0.0
+    if mine:
+        t_off = np.concatenate([[0], np.cumsum([T_all[i] for i in mine])]).astype(np.int64)
+        l_off = np.concatenate([[0], np.cumsum([len(labs[i]) for i in mine])]).astype(np.int64)
+        labels = np.concatenate([labs[i] for i in mine]) if mine else np.zeros(0, np.int32)
+        if any(T_all[i] == 0 for i in mine):   # beams[-1] on an empty list, align.py:100
+            raise IndexError("list index out of range")
+        # (align_fn: the multi-rank CPU tests replace the CUDA plan; then no pinned memory either)
+        batch = (_PinnedPool.array((int(t_off[-1]), V)) if align_fn is None
+                 else np.empty((int(t_off[-1]), V), np.float32))
+        t0 = time.perf_counter()
+
+        def load(n):
+            dst = batch[int(t_off[n]):int(t_off[n + 1])]
+            npz_read_into(todo[mine[n]][0], dst, info=infos[mine[n]])
+            if not device_log_softmax:
+                dst[...] = log_softmax(dst)
+        with ThreadPoolExecutor(max(1, io_threads)) as ex:
+            list(ex.map(load, range(len(mine))))
+        t_read = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        if align_fn is not None:
+            path, lab, sc, _, status = align_fn(batch, t_off, labels, l_off, V, beam_size, max_move, 0)
+        else:
+            with AlignPlan(t_off, labels, l_off, V, beam_size, max_move, device=_current_device()) as plan:
+                path, lab, sc, _, status = plan.run_host(batch, logits=device_log_softmax)
+        t_align = time.perf_counter() - t0
+        t0 = time.perf_counter()
+
+        def save(n):
+            a, b = int(t_off[n]), int(t_off[n + 1])
+            np.savez(todo[mine[n]][2], best_path=path[a:b], best_labels=lab[a:b], best_scores=sc[a:b])
+        good = [n for n in range(len(mine)) if status[n] == ST_OK]
+        for n in range(len(mine)):
+            if status[n] != ST_OK:
+                first_bad = first_bad or int(status[n])
+            elif verbose:
+                print(f'Writing {todo[mine[n]][2]}')
+        with ThreadPoolExecutor(max(1, io_threads)) as ex:
+            list(ex.map(save, good))
+        written = [todo[mine[n]][2] for n in good]
+        t_write = time.perf_counter() - t0
+    if timings is not None:
+        timings.update(read_and_normalise_s=t_read, plan_and_align_s=t_align, write_s=t_write,
+                       total_s=time.perf_counter() - t_start, frames=int(sum(T_all[i] for i in mine)),
+                       chapters=len(mine))
+    if world > 1:
+        import torch.distributed as dist
+        parts = [None] * world if rank == 0 else None
+        dist.gather_object((written, first_bad), parts, dst=0)
+        if rank != 0:
+            return []
+        order = {bf: k for k, (_, _, bf) in enumerate(todo)}
+        written = sorted((bf for w, _ in parts for bf in w), key=order.get)
+        first_bad = next((b for _, b in parts if b != ST_OK), ST_OK)
     raise_for_status(first_bad, V)
     return written
 

@@ -18,6 +18,7 @@
 #include "kab_common.cuh"
 #include "kab_compact.cuh"
 #include "kab_generic.cuh"
+#include "kab_softmax.cuh"
 #include "kab_warp.cuh"
 
 namespace {
@@ -600,8 +601,38 @@ int kab_plan_run_device(kab_plan *pl, const float *d_log_probs, int32_t *d_best_
   return KAB_OK;
 }
 
-int kab_plan_run_host(kab_plan *pl, const float *h_log_probs, int32_t *h_best_path, int32_t *h_best_labels,
-                      float *h_best_scores, float *h_final_score, int32_t *h_status) {
+int kab_log_softmax_device(const float *d_logits, float *d_log_probs, int64_t n_rows, int32_t V, void *stream_) {
+  if (n_rows < 0 || V < 1) return KAB_E_BAD_ARG;
+  if (n_rows == 0) return KAB_OK;
+  if (!d_logits || !d_log_probs) return KAB_E_BAD_ARG;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int dev = 0, sms = 0;
+  KAB_CUDA(cudaGetDevice(&dev));
+  KAB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  if (V <= KAB_SM_MAX_V) {
+    const size_t smem = (size_t)KAB_SM_ROWS * (V | 1) * sizeof(float);
+    const int64_t n_tiles = (n_rows + KAB_SM_ROWS - 1) / KAB_SM_ROWS;
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / (smem + 1024)));
+    const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, (int64_t)sms * per_sm);
+    const int vec_ok = ((uintptr_t)d_logits % 16 == 0 && (uintptr_t)d_log_probs % 16 == 0) ? 1 : 0;
+    if (V == 39) {
+      KAB_CUDA(cudaFuncSetAttribute(kab_log_softmax_kernel<39>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kab_log_softmax_kernel<39><<<grid, KAB_SM_ROWS, smem, stream>>>(d_logits, d_log_probs, n_rows, V, vec_ok);
+    } else {
+      KAB_CUDA(cudaFuncSetAttribute(kab_log_softmax_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kab_log_softmax_kernel<0><<<grid, KAB_SM_ROWS, smem, stream>>>(d_logits, d_log_probs, n_rows, V, vec_ok);
+    }
+  } else {
+    const unsigned grid = (unsigned)std::min<int64_t>((n_rows + 7) / 8, (int64_t)sms * 8);
+    kab_log_softmax_wide_kernel<<<grid, 256, 0, stream>>>(d_logits, d_log_probs, n_rows, V);
+  }
+  KAB_CUDA(cudaGetLastError());
+  return KAB_OK;
+}
+
+static int run_host_impl(kab_plan *pl, const float *h_log_probs, int32_t *h_best_path, int32_t *h_best_labels,
+                         float *h_best_scores, float *h_final_score, int32_t *h_status, bool logits,
+                         float *h_lp_out) {
   if (!pl) return KAB_E_BAD_ARG;
   if (pl->B == 0) return KAB_OK;
   if (!h_log_probs || !h_best_path || !h_best_labels || !h_best_scores || !h_status) return KAB_E_BAD_ARG;
@@ -660,8 +691,11 @@ int kab_plan_run_host(kab_plan *pl, const float *h_log_probs, int32_t *h_best_pa
   if (pl->segs.empty()) {  // small batch: one copy in, one run, one copy out
     cudaStream_t s = pl->stream;
     KAB_CUDA(cudaMemcpyAsync(pl->d_lp, h_log_probs, n * V * 4, cudaMemcpyHostToDevice, s));
-    int rc = kab_plan_run_device(pl, pl->d_lp, pl->d_path, pl->d_lab, pl->d_sc, pl->d_fs, pl->d_st, s);
+    int rc = KAB_OK;
+    if (logits && (rc = kab_log_softmax_device(pl->d_lp, pl->d_lp, (int64_t)n, pl->V, s)) != KAB_OK) return rc;
+    rc = kab_plan_run_device(pl, pl->d_lp, pl->d_path, pl->d_lab, pl->d_sc, pl->d_fs, pl->d_st, s);
     if (rc != KAB_OK) return rc;
+    if (h_lp_out) KAB_CUDA(cudaMemcpyAsync(h_lp_out, pl->d_lp, n * V * 4, cudaMemcpyDeviceToHost, s));
     KAB_CUDA(cudaMemcpyAsync(h_best_path, pl->d_path, n * 4, cudaMemcpyDeviceToHost, s));
     KAB_CUDA(cudaMemcpyAsync(h_best_labels, pl->d_lab, n * 4, cudaMemcpyDeviceToHost, s));
     KAB_CUDA(cudaMemcpyAsync(h_best_scores, pl->d_sc, n * 4, cudaMemcpyDeviceToHost, s));
@@ -678,11 +712,16 @@ int kab_plan_run_host(kab_plan *pl, const float *h_log_probs, int32_t *h_best_pa
     KAB_CUDA(cudaMemcpyAsync(pl->d_lp + t0 * V, h_log_probs + t0 * V, nk * V * 4, cudaMemcpyHostToDevice, pl->s_in));
     KAB_CUDA(cudaEventRecord(pl->ev_in[k], pl->s_in));
     KAB_CUDA(cudaStreamWaitEvent(pl->stream, pl->ev_in[k], 0));
-    int rc = kab_plan_run_device(c, pl->d_lp + t0 * V, pl->d_path + t0, pl->d_lab + t0, pl->d_sc + t0,
-                                 pl->d_fs + b0, pl->d_st + b0, pl->stream);
+    int rc = KAB_OK;
+    if (logits && (rc = kab_log_softmax_device(pl->d_lp + t0 * V, pl->d_lp + t0 * V, (int64_t)nk, pl->V, pl->stream)) != KAB_OK)
+      return rc;
+    rc = kab_plan_run_device(c, pl->d_lp + t0 * V, pl->d_path + t0, pl->d_lab + t0, pl->d_sc + t0,
+                             pl->d_fs + b0, pl->d_st + b0, pl->stream);
     if (rc != KAB_OK) return rc;
     KAB_CUDA(cudaEventRecord(pl->ev_cmp[k], pl->stream));
     KAB_CUDA(cudaStreamWaitEvent(pl->s_out, pl->ev_cmp[k], 0));
+    if (h_lp_out)
+      KAB_CUDA(cudaMemcpyAsync(h_lp_out + t0 * V, pl->d_lp + t0 * V, nk * V * 4, cudaMemcpyDeviceToHost, pl->s_out));
     KAB_CUDA(cudaMemcpyAsync(h_best_path + t0, pl->d_path + t0, nk * 4, cudaMemcpyDeviceToHost, pl->s_out));
     KAB_CUDA(cudaMemcpyAsync(h_best_labels + t0, pl->d_lab + t0, nk * 4, cudaMemcpyDeviceToHost, pl->s_out));
     KAB_CUDA(cudaMemcpyAsync(h_best_scores + t0, pl->d_sc + t0, nk * 4, cudaMemcpyDeviceToHost, pl->s_out));
@@ -693,6 +732,18 @@ int kab_plan_run_host(kab_plan *pl, const float *h_log_probs, int32_t *h_best_pa
   KAB_CUDA(cudaStreamSynchronize(pl->s_out));
   KAB_CUDA(cudaStreamSynchronize(pl->stream));
   return KAB_OK;
+}
+
+int kab_plan_run_host(kab_plan *pl, const float *h_log_probs, int32_t *h_best_path, int32_t *h_best_labels,
+                      float *h_best_scores, float *h_final_score, int32_t *h_status) {
+  return run_host_impl(pl, h_log_probs, h_best_path, h_best_labels, h_best_scores, h_final_score, h_status, false,
+                       nullptr);
+}
+
+int kab_plan_run_host_logits(kab_plan *pl, const float *h_logits, int32_t *h_best_path, int32_t *h_best_labels,
+                             float *h_best_scores, float *h_final_score, int32_t *h_status, float *h_log_probs) {
+  return run_host_impl(pl, h_logits, h_best_path, h_best_labels, h_best_scores, h_final_score, h_status, true,
+                       h_log_probs);
 }
 
 int kab_ctc_best_path(const float *log_probs, int64_t T, int32_t V, const int32_t *labels, int64_t L,

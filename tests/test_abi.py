@@ -35,7 +35,8 @@ def test_reference_signatures():
     sig = inspect.signature(align.ctc_best_path)
     assert list(sig.parameters)[:4] == ["log_probs", "labels", "beam_size", "max_move"]
     assert sig.parameters["beam_size"].default == 1000 and sig.parameters["max_move"].default == 4
-    assert list(inspect.signature(align.best_path).parameters) == ["input_file", "voca_file", "output_file"]
+    assert list(inspect.signature(align.best_path).parameters)[:3] == ["input_file", "voca_file", "output_file"]
+    assert inspect.signature(align.best_path).parameters["device_log_softmax"].default is False
 
 
 def test_no_cpu_fallback():
@@ -76,3 +77,29 @@ def test_transcript_labels(tmp_path):
     p = tmp_path / "x.voca.txt"
     p.write_text("こん|k o N\nにちは|n i ch i w a .\n")
     assert align.read_transcript_labels(str(p)).tolist() == [18, 24, 1, 22, 15, 6, 15, 36, 2]
+
+
+def test_npz_wire_format(tmp_path):
+    """{data, indices} archives as np.savez writes them (preprocess.py:12-35,
+    train.py:228) are read straight into a caller-provided buffer; compressed archives and other
+    dtypes fall back to np.load."""
+    from kokoro_align_b200 import align
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((777, 39)).astype(np.float32)
+    idx = np.array([300, 777], np.int32)
+    np.savez(tmp_path / "stored.npz", indices=idx, data=x)
+    np.savez_compressed(tmp_path / "deflated.npz", indices=idx, data=x)
+    np.savez(tmp_path / "f64.npz", indices=idx, data=x.astype(np.float64))
+    shape, dtype, off = align.npz_member_info(str(tmp_path / "stored.npz"))
+    assert shape == (777, 39) and dtype == np.float32 and off is not None
+    with open(tmp_path / "stored.npz", "rb") as f:
+        f.seek(off)
+        assert f.read(x.nbytes) == x.tobytes()
+    assert align.npz_member_info(str(tmp_path / "deflated.npz"))[2] is None
+    for name in ("stored", "deflated", "f64"):
+        dst = np.full((777, 39), np.nan, np.float32)
+        align.npz_read_into(str(tmp_path / f"{name}.npz"), dst)
+        assert dst.tobytes() == x.tobytes()
+    assert align.npz_member_info(str(tmp_path / "stored.npz"), "indices")[0] == (2,)
+    with pytest.raises(ValueError):
+        align.npz_read_into(str(tmp_path / "stored.npz"), np.empty((5, 39), np.float32))

@@ -75,6 +75,63 @@ def test_sharded_alignment_world2():
     assert shards == list(range(len(lps)))          # every lattice exactly once
 
 
+def _files_worker(rank, world, port, q, d):
+    import torch.distributed as dist
+    from kokoro_align_b200 import align
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n = 7
+    lf = [os.path.join(d, f"c{k}.logits.npz") for k in range(n)]
+    vf = [os.path.join(d, f"c{k}.voca.txt") for k in range(n)]
+    bf = [os.path.join(d, f"c{k}.best_path.npz") for k in range(n)]
+    t = {}
+    written = align.best_path_files(lf, vf, bf, verbose=False, align_fn=_oracle_align, timings=t)
+    q.put((rank, written, t["chapters"]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_best_path_files_world2(tmp_path):
+    """The per-book entry under world_size 2: every rank reads, aligns (oracle stand-in) and
+    writes its own LPT shard of the chapters; rank 0 returns all written paths in order; the
+    files equal the single-lattice oracle on the host-normalised logits."""
+    from kokoro_align_b200 import align
+    from oracle import ctc_oracle
+    rng = np.random.default_rng(44)
+    d = str(tmp_path)
+    Ts = [400, 90, 1500, 33, 800, 260, 1]
+    np.savez(os.path.join(d, "c3.best_path.npz"), best_path=np.zeros(1, np.int32))   # exists: skipped
+    for k, T in enumerate(Ts):
+        np.savez(os.path.join(d, f"c{k}.logits.npz"), data=(rng.standard_normal((T, 39)) * 3).astype(np.float32),
+                 indices=np.array([T], np.int32))
+        with open(os.path.join(d, f"c{k}.voca.txt"), "w") as f:
+            for _ in range(max(1, T // 60) if T > 1 else 0):
+                f.write("t|k o k o r o\n")
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_files_worker, args=(r, world, port, q, d)) for r in range(world)]
+    for p in procs:
+        p.start()
+    outs = dict((o[0], o[1:]) for o in (q.get(timeout=120) for _ in range(world)))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    expect = [os.path.join(d, f"c{k}.best_path.npz") for k in range(7) if k != 3]
+    assert outs[0][0] == expect and outs[1][0] == []
+    assert outs[0][1] + outs[1][1] == 6 and outs[0][1] > 0 and outs[1][1] > 0
+    for k in (0, 1, 2, 4, 5, 6):
+        with np.load(os.path.join(d, f"c{k}.logits.npz")) as f:
+            lp = align.log_softmax(f["data"])
+        lab = align.read_transcript_labels(os.path.join(d, f"c{k}.voca.txt"))
+        rp, rl, rs = ctc_oracle.ctc_best_path(lp, lab)
+        with np.load(os.path.join(d, f"c{k}.best_path.npz")) as f:
+            assert f["best_path"].dtype == np.int32 and f["best_scores"].dtype == np.float32
+            assert f["best_path"].tolist() == rp.tolist() and f["best_labels"].tolist() == rl.tolist()
+            assert f["best_scores"].tobytes() == rs.tobytes()
+
+
 def test_lpt_partition_properties():
     from kokoro_align_b200 import parallel
     rng = np.random.default_rng(0)
