@@ -254,7 +254,6 @@ def main():
     barrier()
     step_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
     total_ms = max_over_ranks(ev[0].elapsed_time(ev[args.steps]))
-    clocks = sampler.stop() if rank == 0 else None
     cells_all = sum_over_ranks(cells_eval)
     nominal_all = sum_over_ranks(cells_nominal)
     value = cells_all * args.steps / (total_ms * 1e-3)
@@ -270,7 +269,29 @@ def main():
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = cells_all * args.steps / e2e_s
+    clocks = sampler.stop() if rank == 0 else None   # sampled over both timed regions
     np.testing.assert_array_equal(h_out_np[0], outs[0].cpu().numpy())
+
+    # ---- secondary: the same call on RAW LOGITS, align.py:116-117 on the device (kab_softmax.cuh)
+    for _ in range(2):
+        plan.run_host(h_lp.numpy(), out=h_out_np, logits=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        plan.run_host(h_lp.numpy(), out=h_out_np, logits=True)
+    barrier()
+    e2e_logits_s = max_over_ranks(time.perf_counter() - t0)
+    sm_ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    d_tmp = torch.empty_like(d_lp)
+    align.log_softmax_torch(d_lp, out=d_tmp)
+    sm_ev[0].record()
+    for _ in range(args.steps):
+        align.log_softmax_torch(d_lp, out=d_tmp)
+    sm_ev[1].record()
+    torch.cuda.synchronize()
+    softmax_ms = sm_ev[0].elapsed_time(sm_ev[1]) / args.steps
+    del d_tmp
+    plan.run_host(h_lp.numpy(), out=h_out_np)   # restore the log-prob results for the parity spot check
 
     # ---- CPU baseline (rank 0, bounded sample of the same workload, numpy port, 1 core)
     cpu = None
@@ -308,6 +329,11 @@ def main():
                        "parallelism": f"{world} independent ranks, no collective on the data path"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_frames * 39 * 4,
                     "d2h_bytes_per_step": n_frames * 12 + plan.B * 8, "ms_per_step": e2e_s / args.steps * 1e3},
+            "e2e_raw_logits": {"value": cells_all * args.steps / e2e_logits_s, "unit": UNIT,
+                               "ms_per_step": e2e_logits_s / args.steps * 1e3,
+                               "note": "same call on raw logits, log-softmax (align.py:116-117) on the device",
+                               "log_softmax_kernel_ms": softmax_ms,
+                               "log_softmax_gbs": 8.0 * n_frames * 39 / (softmax_ms * 1e-3) / 1e9},
             "gpu_launches": int(info.kernel_launches) * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,

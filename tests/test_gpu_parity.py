@@ -265,6 +265,21 @@ def test_config4_banded_million_frames(kab):
     assert d.min() >= 0 and d.max() <= 3
 
 
+def test_log_probs_beyond_2_gib(kab):
+    """Maximum sizes: a batch whose log-probs exceed 2^31 bytes (30 000 segments, 14 M frames,
+    2.2 GB) with a band lattice BEHIND the 2 GiB mark: every byte offset of the warp / band
+    kernels, the staging descriptors and the pipelined host path must be 64-bit.  Bit-exact
+    against the C oracle."""
+    from kokoro_align_b200 import synth
+    T, L = synth.segment_lengths(30000, seed=6100)
+    T = np.concatenate([T, [20011]])
+    L = np.concatenate([L, [2801]])
+    lp, t_off, labels, l_off = synth.make_batch_fast(T, L, seed=6101)
+    assert int(t_off[-2]) * 39 * 4 > 2 ** 31
+    info = _compare_batch(kab, lp, t_off, labels, l_off, threads=16)
+    assert info.n_class[0] == 30000 and info.n_class[1] == 1
+
+
 def test_best_path_files_batch(kab, tmp_path, capsys):
     """The per-book loop (run_example.py:247-254) as one batch: same npz files as the per-file
     best_path(), existing outputs skipped with the reference's message."""

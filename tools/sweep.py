@@ -20,8 +20,10 @@ if os.path.exists("MEASURED_PEAKS.json"):
     peak = json.load(open("MEASURED_PEAKS.json"))["hbm_gbs"]
 out = []
 points = [(T, L, 39) for T in Ts for L in Ls]
-# wide vocabularies (whole rows are staged up to V = 512; V = 4096 runs in the generic kernel)
-points += [(1000, 100, 256), (10000, 1000, 256), (1000, 100, 512)] + ([] if quick else [(1000, 100, 4096)])
+# wide vocabularies (whole rows are staged up to V = 512)
+# (V = 4096: compact per-lattice copy of the used columns, kab_compact.cuh)
+wide_v = [(1000, 100, 256), (10000, 1000, 256), (1000, 100, 512), (1000, 100, 4096), (10000, 1000, 4096)]
+points = wide_v if "--wide-v" in sys.argv else points + ([] if quick else wide_v)
 for T, L, V in points:
     if True:
         S = 2 * L + 1
