@@ -615,7 +615,23 @@ int kab_log_softmax_device(const float *d_logits, float *d_log_probs, int64_t n_
     const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / (smem + 1024)));
     const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, (int64_t)sms * per_sm);
     const int vec_ok = ((uintptr_t)d_logits % 16 == 0 && (uintptr_t)d_log_probs % 16 == 0) ? 1 : 0;
-    if (V == 39) {
+    static const bool no_tma = getenv("KAB_SOFTMAX_NO_TMA") != nullptr;  // development knob
+    if (V == 39 && vec_ok && !no_tma) {
+      // full tiles through the bulk-copy pipeline (one persistent CTA per SM), the tail below
+      const int64_t n_full = n_rows / KAB_SM_ROWS;
+      if (n_full > 0) {
+        const size_t smem_t = 128 + (size_t)KAB_SMT_BUFS * KAB_SM_ROWS * 39 * sizeof(float);
+        KAB_CUDA(cudaFuncSetAttribute(kab_log_softmax_tma_kernel<39>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+        kab_log_softmax_tma_kernel<39><<<(unsigned)std::min<int64_t>(n_full, sms), KAB_SM_ROWS, smem_t, stream>>>(
+            d_logits, d_log_probs, n_full);
+      }
+      const int64_t tail = n_rows - n_full * KAB_SM_ROWS;
+      if (tail > 0) {
+        KAB_CUDA(cudaFuncSetAttribute(kab_log_softmax_kernel<39>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kab_log_softmax_kernel<39><<<1, KAB_SM_ROWS, smem, stream>>>(d_logits + n_full * KAB_SM_ROWS * 39,
+                                                                      d_log_probs + n_full * KAB_SM_ROWS * 39, tail, V, 1);
+      }
+    } else if (V == 39) {
       KAB_CUDA(cudaFuncSetAttribute(kab_log_softmax_kernel<39>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       kab_log_softmax_kernel<39><<<grid, KAB_SM_ROWS, smem, stream>>>(d_logits, d_log_probs, n_rows, V, vec_ok);
     } else {

@@ -98,6 +98,10 @@ __device__ __forceinline__ void kab_bulk_g2s_hint(void *dst, const void *src, ui
       : "memory");
 }
 __device__ __forceinline__ void kab_fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// shared-memory-only form: SASS FENCE.VIEW.ASYNC.S without the MEMBAR.ALL.GPU of the generic one
+__device__ __forceinline__ void kab_fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
 
 // ---------------------------------------------------------------- emission staging
 // Frames [f0, f0+nf) of a lattice are rows of V floats starting at byte b0 of lp.  Rows are only

@@ -18,6 +18,9 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "kab_band.cuh"    // kab_bulk_s2g
+#include "kab_bandp.cuh"   // kab_bulk_wait_read1
+#include "kab_common.cuh"  // mbarrier + bulk-copy helpers
 
 #define KAB_SM_ROWS 256     // rows per tile = threads per CTA
 #define KAB_SM_MAX_V 128    // widest row of the thread-per-row kernel
@@ -42,6 +45,89 @@ __device__ __forceinline__ float kab_np_rowsum(int n, F f) {
                         __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
   for (; i < n; ++i) res = __fadd_rn(res, f(i));
   return res;
+}
+
+// the same with a compile-time length (fully unrolled: f's operands stay in registers)
+template <int N, class F>
+__device__ __forceinline__ float kab_np_rowsum_ct(F f) {
+  static_assert(N >= 8 && N <= 128, "");
+  float r[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) r[j] = f(j);
+#pragma unroll
+  for (int i = 8; i + 8 <= N; i += 8) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(r[j], f(i + j));
+  }
+  float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                        __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+#pragma unroll
+  for (int i = N - N % 8; i < N; ++i) res = __fadd_rn(res, f(i));
+  return res;
+}
+
+// ---- V = 39 (the reference's vocabulary, encoder.py:11) and 16-byte aligned buffers: persistent
+// CTAs, one per SM, over full tiles of KAB_SM_ROWS rows (39 936 B, contiguous in HBM) in a ring of
+// KAB_SMT_BUFS shared-memory buffers.  Thread 0 keeps two tile loads in flight (1-D bulk copies
+// completing on an mbarrier), every thread normalises one row in registers and writes it back to
+// the same buffer, and the tile leaves by a bulk store; a buffer is reloaded two iterations after
+// its store was issued (cp.async.bulk.wait_group.read 1), so neither direction ever waits for
+// the other.  The rows behind the last full tile go through kab_log_softmax_kernel.
+#define KAB_SMT_BUFS 4
+template <int V>
+__global__ void __launch_bounds__(KAB_SM_ROWS, 1)
+kab_log_softmax_tma_kernel(const float *in, float *out, int64_t n_tiles) {
+  extern __shared__ __align__(128) unsigned char kab_smt_raw[];
+  uint64_t *bars = reinterpret_cast<uint64_t *>(kab_smt_raw);
+  float *tiles = reinterpret_cast<float *>(kab_smt_raw + 128);
+  constexpr uint32_t TILE_EL = KAB_SM_ROWS * V, TILE_BYTES = TILE_EL * 4;
+  static_assert(TILE_BYTES % 16 == 0 && (V & 1), "");
+  if ((int64_t)blockIdx.x >= n_tiles) return;
+  const int nk = (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+  uint64_t policy;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+  if (threadIdx.x == 0) {
+    for (int b = 0; b < KAB_SMT_BUFS; ++b) kab_mbar_init(&bars[b], 1);
+    kab_fence_mbar_init();
+  }
+  __syncthreads();
+  auto issue = [&](int k) {  // thread 0 only
+    const int64_t tile = blockIdx.x + (int64_t)k * gridDim.x;
+    const int b = k % KAB_SMT_BUFS;
+    kab_mbar_expect_tx(&bars[b], TILE_BYTES);
+    kab_bulk_g2s_hint(tiles + (size_t)b * TILE_EL, in + tile * TILE_EL, TILE_BYTES, &bars[b], policy);
+  };
+  if (threadIdx.x == 0) {
+    issue(0);
+    if (nk > 1) issue(1);
+  }
+  for (int k = 0; k < nk; ++k) {
+    const int b = k % KAB_SMT_BUFS;
+    if (threadIdx.x == 0 && k + 2 < nk) {
+      if (k >= 2) kab_bulk_wait_read1();  // the store of tile k-2 has left buffer (k+2) % BUFS
+      issue(k + 2);
+    }
+    kab_mbar_wait(&bars[b], (uint32_t)(k / KAB_SMT_BUFS) & 1u);
+    float *row = tiles + (size_t)b * TILE_EL + threadIdx.x * V;
+    float x[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) x[i] = row[i];
+    const float mean = __fdiv_rn(kab_np_rowsum_ct<V>([&](int i) { return x[i]; }), (float)V);
+    const float se = kab_np_rowsum_ct<V>([&](int i) {
+      x[i] = __fsub_rn(x[i], mean);
+      return expf(x[i]);
+    });
+    const float lse = logf(se);
+#pragma unroll
+    for (int i = 0; i < V; ++i) row[i] = __fsub_rn(x[i], lse);
+    kab_fence_proxy_async_smem();  // the rows -> visible to the bulk store
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int64_t tile = blockIdx.x + (int64_t)k * gridDim.x;
+      kab_bulk_s2g(out + tile * TILE_EL, tiles + (size_t)b * TILE_EL, TILE_BYTES);
+    }
+  }
+  if (threadIdx.x == 0) kab_bulk_wait_read0();  // shared memory must outlive the last stores' reads
 }
 
 // VT > 0: compile-time vocabulary (39: the reference's), 0: runtime V <= KAB_SM_MAX_V
