@@ -14,6 +14,7 @@
 
 #include "kab_band.cuh"
 #include "kab_bandp.cuh"
+#include "kab_btpar.cuh"
 #include "kab_wide.cuh"
 #include "kab_common.cuh"
 #include "kab_compact.cuh"
@@ -84,6 +85,12 @@ struct kab_plan {
   int32_t *d_status_init = nullptr;
   unsigned char *d_wide_ws = nullptr;  // wide kernel: per-lattice control words and neighbour FIFOs
   int64_t wide_ws_bytes = 0;
+  // parallel backtrack of the cluster band kernel (kab_btpar.cuh)
+  std::vector<KabBtMeta> bt_meta;
+  KabBtMeta *d_bt_meta = nullptr;
+  int32_t *d_bt_maps = nullptr, *d_bt_entry = nullptr, *d_end_state = nullptr;
+  int64_t bt_map_ints = 0;
+  int32_t bt_blocks = 0, bt_max_wl = 0;
   unsigned char *d_band_fifo = nullptr;  // cluster band kernel: per-lattice progress counters and FIFOs
   int64_t band_fifo_bytes = 0;
   // launch geometry
@@ -113,7 +120,7 @@ int plan_free(kab_plan *pl) {
   cudaSetDevice(pl->device);
   for (int q = 0; q < N_QUEUES; ++q) cudaFree(pl->d_lists[q]);
   cudaFree(pl->d_col16); cudaFree(pl->d_raw); cudaFree(pl->d_bp); cudaFree(pl->d_scratch);
-  cudaFree(pl->d_queue); cudaFree(pl->d_status_init); cudaFree(pl->d_wide_ws); cudaFree(pl->d_band_fifo); cudaFree(pl->d_gather); cudaFree(pl->d_lpc);
+  cudaFree(pl->d_queue); cudaFree(pl->d_status_init); cudaFree(pl->d_wide_ws); cudaFree(pl->d_band_fifo); cudaFree(pl->d_bt_meta); cudaFree(pl->d_bt_maps); cudaFree(pl->d_bt_entry); cudaFree(pl->d_end_state); cudaFree(pl->d_gather); cudaFree(pl->d_lpc);
   cudaFree(pl->d_lp); cudaFree(pl->d_path); cudaFree(pl->d_lab); cudaFree(pl->d_st);
   cudaFree(pl->d_sc); cudaFree(pl->d_fs);
   if (pl->stream) cudaStreamDestroy(pl->stream);
@@ -351,6 +358,22 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
       return a.T > b2.T;
     });
 
+  // parallel backtrack of the cluster band kernel: per-lattice block maps (KAB_BAND_SERIAL_BT=1
+  // keeps the in-kernel single-thread walker: development / comparison)
+  if (!pl->lists[Q_BAND].empty() && pl->band_nc > 0 && !getenv("KAB_BAND_SERIAL_BT")) {
+    for (const KabLattice &d : pl->lists[Q_BAND]) {
+      KabBtMeta m{};
+      m.map_off = pl->bt_map_ints;
+      m.first_block = pl->bt_blocks;
+      m.n_blocks = (d.T + KAB_BT_BLOCK - 1) / KAB_BT_BLOCK;
+      m.wl = (int32_t)align_up(std::min<int64_t>(W, 2 * (int64_t)d.L + 1), 32);
+      pl->bt_map_ints += (int64_t)m.n_blocks * m.wl;
+      pl->bt_blocks += m.n_blocks;
+      pl->bt_max_wl = std::max(pl->bt_max_wl, m.wl);
+      pl->bt_meta.push_back(m);
+    }
+  }
+
   // ---- device allocations
   int rc = KAB_OK;
   auto up = [&](void **dst, const void *src, size_t bytes) -> int {
@@ -394,6 +417,12 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
       }
       pl->grid[Q_WARP] = (int)std::min<int64_t>(ctas, (int64_t)pl->sm_count * std::max(occ, 1));
     }
+    if (!pl->bt_meta.empty()) {
+      if ((rc = up((void **)&pl->d_bt_meta, pl->bt_meta.data(), pl->bt_meta.size() * sizeof(KabBtMeta)))) break;
+      if ((e = cudaMalloc((void **)&pl->d_bt_maps, (size_t)pl->bt_map_ints * 4)) != cudaSuccess) { rc = cuda_fail(e, "cudaMalloc(backtrack maps)"); break; }
+      if ((e = cudaMalloc((void **)&pl->d_bt_entry, (size_t)pl->bt_blocks * 4)) != cudaSuccess) { rc = cuda_fail(e, "cudaMalloc(backtrack entries)"); break; }
+      if ((e = cudaMalloc((void **)&pl->d_end_state, (size_t)pl->B * 4)) != cudaSuccess) { rc = cuda_fail(e, "cudaMalloc(end states)"); break; }
+    }
     if (!pl->lists[Q_BAND].empty() && pl->band_nc > 0) {
       if ((e = cudaMalloc((void **)&pl->d_band_fifo, (size_t)pl->band_fifo_bytes)) != cudaSuccess) { rc = cuda_fail(e, "cudaMalloc(band FIFOs)"); break; }
       const KabBandpGeom geo = kab_bandp_geom(pl->stage_bytes);
@@ -435,6 +464,9 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
                          (pl->d_raw ? pl->total_L * 4 : 0) + B * (int64_t)sizeof(KabLattice);
   info.kernel_launches = 0;
   for (int q = 0; q < N_QUEUES; ++q) info.kernel_launches += pl->lists[q].empty() ? 0 : 1;
+  if (!pl->bt_meta.empty()) info.kernel_launches += 2;  // kab_bt_maps_kernel, kab_bt_stitch_kernel
+  if (pl->Vc)                                          // kab_compact_kernel, kab_expand_labels_kernel
+    for (int q : {Q_WARP, Q_BAND, Q_WIDE}) info.kernel_launches += pl->lists[q].empty() ? 0 : 2;
   *out = pl;
   return KAB_OK;
 }
@@ -535,8 +567,17 @@ int kab_plan_run_device(kab_plan *pl, const float *d_log_probs, int32_t *d_best_
       cfg.dynamicSmemBytes = pl->smem[Q_BAND];
       cfg.stream = stream;
       cfg.attrs = at; cfg.numAttrs = 1;
+      pb.end_state = pl->d_end_state;  // nullptr: the kernel walks back itself
       KAB_CUDA(cudaLaunchKernelEx(&cfg, kab_bandp_kernel, (const KabLattice *)pl->d_lists[Q_BAND],
                                   (int)pl->lists[Q_BAND].size(), pb));
+      if (pl->d_end_state) {
+        const int n_band = (int)pl->lists[Q_BAND].size(), nwt = KAB_BP_CW * pl->band_nc;
+        const dim3 mg((unsigned)pl->bt_blocks, (unsigned)((pl->bt_max_wl + KAB_BT_THREADS - 1) / KAB_BT_THREADS));
+        kab_bt_maps_kernel<<<mg, KAB_BT_THREADS, 0, stream>>>(pl->d_lists[Q_BAND], pl->d_bt_meta, n_band, pl->d_bp,
+                                                              d_status, pl->d_bt_maps, pl->W, nwt);
+        kab_bt_stitch_kernel<<<n_band, 1024, 0, stream>>>(pl->d_lists[Q_BAND], pl->d_bt_meta, pb, pl->d_end_state,
+                                                          pl->d_bt_maps, pl->d_bt_entry, nwt);
+      }
     } else if (pl->band_nw <= 16)
       kab_band_kernel<512><<<pl->grid[Q_BAND], pl->band_nw * 32, pl->smem[Q_BAND], stream>>>(
           pl->d_lists[Q_BAND], (int)pl->lists[Q_BAND].size(), pb);

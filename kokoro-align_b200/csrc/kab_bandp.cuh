@@ -582,7 +582,9 @@ __global__ void __launch_bounds__(KAB_BP_THREADS, 1)
 #ifdef KAB_BANDP_TIMING
       const long long tm_bt0 = clock64();
 #endif
-      if (status == 0) {
+      if (status == 0 && p.end_state) {
+        if (tid == 0) p.end_state[lat.index] = v;  // traceback by kab_bt_maps_kernel / kab_bt_stitch_kernel
+      } else if (status == 0) {
         // ---- backtrack (== flush_determined_path, align.py:21-40), CTA 0 only.  Blocks of FBK frames
         // = FBK / 8 groups of 256 bytes per region; the walker (one thread) reads the 8 frames of a
         // group for its byte column and the column below as two 64-bit words and then runs on

@@ -1,0 +1,129 @@
+// kab_btpar.cuh -- parallel backtrack for the cluster band kernel (kab_bandp.cuh).
+//
+// The traceback of align.py:21-40 / :99-102 is a chain of T dependent steps
+//     v_{t-1} = v_t - move[t][v_t]
+// and the in-kernel walker of kab_bandp.cuh spends ~78 cycles on each: a quarter of the time of a
+// long lattice, on ONE thread, while the rest of the GPU idles (a plan that uses this kernel has
+// at most a few dozen lattices).  The steps are function compositions, so they parallelise
+// exactly -- no speculation:
+//   1. kab_bt_maps_kernel: the frames are cut into blocks of KAB_BT_BLOCK.  For every block and
+//      EVERY state of the window at the block's last frame, one thread walks the block backwards
+//      and records where it leaves it: maps[block][v - lo] = state at the frame before the block.
+//      T x W steps in total (as many as the forward pass has cells), spread over the whole GPU.
+//      Walkers that start in inactive states produce values nobody looks up (moves are clamped so
+//      that they stay inside the workspace).
+//   2. kab_bt_stitch_kernel (one CTA per lattice): thread 0 composes the maps from the forced end
+//      state down -- T / KAB_BT_BLOCK dependent table look-ups -- which yields the true entry
+//      state of every block; then the threads re-walk the blocks from their entry states, all
+//      blocks at once, and write best_path / best_labels / best_scores (align.py:105-107).
+// Backpointer layout (written by kab_bandp_kernel): byte of (frame t, state v) at
+//     bp[((reg * n_groups + t / 8) * 32 + col) * 8 + t % 8],   slot = v mod R, reg = slot / 104,
+//     col = (slot % 104) / 4, move = (byte >> 2 * (slot & 3)) & 3.
+#pragma once
+#include "kab_band.cuh"
+#include "kab_common.cuh"
+
+#define KAB_BT_BLOCK 512    // frames per block
+#define KAB_BT_THREADS 128  // threads per CTA of the map kernel (= entry states per CTA)
+
+struct KabBtMeta {       // one per lattice of the band list (same order)
+  int64_t map_off;       // first int32 of this lattice's maps
+  int32_t first_block;   // prefix sum of n_blocks over the list
+  int32_t n_blocks;
+  int32_t wl;            // map row length: min(W, S) rounded up to 32
+  int32_t pad;
+};
+
+// walker state: state v, its position rs inside ring region reg, that region's backpointer rows
+struct KabBtWalker {
+  int v, rs, reg;
+  const unsigned char *rows;  // bp + reg * n_groups * 256
+  __device__ __forceinline__ void init(int v0, int R, const unsigned char *bp, int n_groups) {
+    v = v0;
+    const int slot = v0 % R;
+    reg = slot / KAB_BAND_OW;
+    rs = slot - reg * KAB_BAND_OW;
+    rows = bp + (size_t)reg * n_groups * 256;
+  }
+  // one frame back; returns the state AT frame t (before the move)
+  __device__ __forceinline__ int step(int t, int NWT, const unsigned char *bp, int n_groups) {
+    const unsigned int byte = rows[(size_t)(t >> 3) * 256 + (rs >> 2) * 8 + (t & 7)];
+    const int at = v;
+    const int mv = min((int)((byte >> (2 * (rs & 3))) & 3u), v);  // (clamp: only garbage walkers hit it)
+    v -= mv;
+    rs -= mv;
+    if (rs < 0) {  // into the region below (a move crosses at most one boundary)
+      rs += KAB_BAND_OW;
+      reg = reg == 0 ? NWT - 1 : reg - 1;
+      rows = bp + (size_t)reg * n_groups * 256;
+    }
+    return at;
+  }
+};
+
+__device__ __forceinline__ int kab_bt_lo(int64_t S, int64_t t, int64_t T, int W) {  // align.py:64
+  const int64_t lo = S * t / T - W / 2;
+  return lo < 0 ? 0 : (int)lo;
+}
+
+// grid.x = total blocks of all lattices, grid.y = chunks of KAB_BT_THREADS entry states
+__global__ void __launch_bounds__(KAB_BT_THREADS)
+kab_bt_maps_kernel(const KabLattice *__restrict__ lats, const KabBtMeta *__restrict__ meta, int n_lat,
+                   const unsigned char *__restrict__ bpw, const int32_t *__restrict__ status, int32_t *__restrict__ maps,
+                   int W, int NWT) {
+  int li = 0;
+  while (li + 1 < n_lat && (int)blockIdx.x >= meta[li + 1].first_block) ++li;
+  const KabLattice lat = lats[li];
+  const KabBtMeta m = meta[li];
+  if (status[lat.index] != 0) return;
+  const int b = (int)blockIdx.x - m.first_block;
+  const int T = lat.T, S = 2 * lat.L + 1, R = KAB_BAND_OW * NWT, n_groups = (T + 7) / 8;
+  const int t0 = b * KAB_BT_BLOCK, te = min(T, t0 + KAB_BT_BLOCK) - 1;
+  const int lo = kab_bt_lo(S, te, T, W), hi = min(lo + W, S);
+  const int j = blockIdx.y * KAB_BT_THREADS + threadIdx.x;
+  if (lo + j >= hi) return;
+  const unsigned char *bp = bpw + lat.bp_off;
+  KabBtWalker w;
+  w.init(lo + j, R, bp, n_groups);
+  for (int t = te; t >= t0; --t) w.step(t, NWT, bp, n_groups);
+  maps[m.map_off + (int64_t)b * m.wl + j] = w.v;
+}
+
+// one CTA per lattice
+__global__ void __launch_bounds__(1024)
+kab_bt_stitch_kernel(const KabLattice *__restrict__ lats, const KabBtMeta *__restrict__ meta, KabParams p,
+                     const int32_t *__restrict__ end_state, const int32_t *__restrict__ maps,
+                     int32_t *__restrict__ entry, int NWT) {
+  const KabLattice lat = lats[blockIdx.x];
+  const KabBtMeta m = meta[blockIdx.x];
+  if (p.status[lat.index] != 0) return;
+  const int T = lat.T, S = 2 * lat.L + 1, W = p.W, V = p.V, R = KAB_BAND_OW * NWT, n_groups = (T + 7) / 8;
+  int32_t *ent = entry + m.first_block;
+  if (threadIdx.x == 0) {  // compose the block maps from the forced end state down
+    int v = end_state[lat.index];
+    for (int b = m.n_blocks - 1; b >= 0; --b) {
+      ent[b] = v;
+      const int te = min(T, (b + 1) * KAB_BT_BLOCK) - 1;
+      v = __ldcg(&maps[m.map_off + (int64_t)b * m.wl + (v - kab_bt_lo(S, te, T, W))]);
+    }
+  }
+  __syncthreads();
+  const unsigned char *bp = p.bp + lat.bp_off;
+  const uint16_t *col16 = p.col16 + lat.col_off;
+  int32_t *out_path = p.best_path + lat.t_off;
+  int32_t *out_lab = p.best_labels + lat.t_off;
+  float *out_sc = p.best_scores + lat.t_off;
+  const float *lp = p.lp + lat.t_off * (int64_t)V;
+  for (int b = threadIdx.x; b < m.n_blocks; b += blockDim.x) {
+    const int t0 = b * KAB_BT_BLOCK, te = min(T, t0 + KAB_BT_BLOCK) - 1;
+    KabBtWalker w;
+    w.init(ent[b], R, bp, n_groups);
+    for (int t = te; t >= t0; --t) {
+      const int pv = w.step(t, NWT, bp, n_groups);
+      const int lab = (pv & 1) ? (int)col16[(pv - 1) >> 1] : 0;
+      out_path[t] = pv;
+      out_lab[t] = lab;                              // align.py:106
+      out_sc[t] = __ldg(&lp[(int64_t)t * V + lab]);  // align.py:107
+    }
+  }
+}

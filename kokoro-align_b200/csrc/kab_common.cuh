@@ -42,6 +42,8 @@ struct KabParams {
   int32_t stage_frames;     // emission frames per bulk-copy stage
   int32_t stage_bytes;      // bytes of one stage buffer (multiple of 16)
   int32_t band_nw;          // warps per CTA of the band kernel
+  int32_t *end_state;       // cluster band kernel: not nullptr = write the forced end state of every lattice
+                            // here ([B]) and leave the traceback to kab_btpar.cuh
   long long *debug;         // development only (KAB_BAND_TIMING builds)
   uint32_t one;             // the value 1, opaque to the compiler (kab_blank_sel / kab_label_sel)
 };

@@ -203,13 +203,18 @@ def test_random_shapes_and_beams(kab, seed):
     _compare_batch(kab, lp, t_off, labels, l_off, beam_size=W)
 
 
-@pytest.mark.parametrize("beam_size,cluster", [(1000, 1), (64, 1), (200, 2), (1000, 0), (64, 0), (300, 0)])
-def test_both_band_kernels(kab, monkeypatch, beam_size, cluster):
+@pytest.mark.parametrize("beam_size,cluster,serial_bt", [(1000, 1, 0), (64, 1, 0), (200, 2, 0), (1000, 1, 1), (200, 2, 1),
+                                                         (1000, 0, 0), (64, 0, 0), (300, 0, 0)])
+def test_both_band_kernels(kab, monkeypatch, beam_size, cluster, serial_bt):
     """The two band kernels against the C oracle, forced through KAB_BAND_CLUSTER: the pipelined
     cluster kernel (kab_bandp.cuh, the default when every lattice gets its own cluster) and the
-    single-CTA kernel (kab_band.cuh, the default for larger batches, = 0 here)."""
+    single-CTA kernel (kab_band.cuh, the default for larger batches, = 0 here).  The cluster
+    kernel with both tracebacks: the parallel block-map composition (kab_btpar.cuh, default) and
+    its own single-thread walker (KAB_BAND_SERIAL_BT=1)."""
     from kokoro_align_b200 import synth
     monkeypatch.setenv("KAB_BAND_CLUSTER", str(cluster))
+    if serial_bt:
+        monkeypatch.setenv("KAB_BAND_SERIAL_BT", "1")
     T = np.array([12000, 7001, 3000, 41, 5003])
     L = np.round(0.14 * T).astype(np.int64)
     L[4] = 1700  # S/T = 0.68: the walker changes warp regions often
