@@ -213,8 +213,7 @@ def test_both_band_kernels(kab, monkeypatch, beam_size, cluster, serial_bt):
     its own single-thread walker (KAB_BAND_SERIAL_BT=1)."""
     from kokoro_align_b200 import synth
     monkeypatch.setenv("KAB_BAND_CLUSTER", str(cluster))
-    if serial_bt:
-        monkeypatch.setenv("KAB_BAND_SERIAL_BT", "1")
+    monkeypatch.setenv("KAB_BAND_SERIAL_BT", str(serial_bt))   # 0 forces the parallel traceback
     T = np.array([12000, 7001, 3000, 41, 5003])
     L = np.round(0.14 * T).astype(np.int64)
     L[4] = 1700  # S/T = 0.68: the walker changes warp regions often
