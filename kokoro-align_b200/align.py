@@ -331,19 +331,21 @@ def best_path_files(logits_files, voca_files, best_path_files, skip_existing=Tru
     except ImportError:
         world, rank = 1, 0
     infos = [npz_member_info(lf) for lf, _, _ in todo]
-    labs = [np.asarray(read_transcript_labels(vf), dtype=np.int32) for _, vf, _ in todo]
     for (shape, _, _), (lf, _, _) in zip(infos, todo):
         if len(shape) != 2 or shape[1] != infos[0][0][1]:
             raise ValueError(f"{lf}: logits must be [T, {infos[0][0][1]}], got {shape}")
     V = int(infos[0][0][1])
     T_all = [int(i[0][0]) for i in infos]
-    mine = [int(i) for i in parallel.shard_batch(T_all, [len(x) for x in labs], rank, world, beam_size)]
+    labs = None
+    if world > 1:   # the LPT shards need the label counts of every chapter
+        labs = [np.asarray(read_transcript_labels(vf), dtype=np.int32) for _, vf, _ in todo]
+        mine = [int(i) for i in parallel.shard_batch(T_all, [len(x) for x in labs], rank, world, beam_size)]
+    else:
+        mine = list(range(len(todo)))
     written, first_bad = [], ST_OK
     t_read = t_norm = t_align = t_write = 0.0
     if mine:
         t_off = np.concatenate([[0], np.cumsum([T_all[i] for i in mine])]).astype(np.int64)
-        l_off = np.concatenate([[0], np.cumsum([len(labs[i]) for i in mine])]).astype(np.int64)
-        labels = np.concatenate([labs[i] for i in mine]) if mine else np.zeros(0, np.int32)
         if any(T_all[i] == 0 for i in mine):   # beams[-1] on an empty list, align.py:100
             raise IndexError("list index out of range")
         # (align_fn: the multi-rank CPU tests replace the CUDA plan; then no pinned memory either)
@@ -357,7 +359,15 @@ def best_path_files(logits_files, voca_files, best_path_files, skip_existing=Tru
             if not device_log_softmax:
                 dst[...] = log_softmax(dst)
         with ThreadPoolExecutor(max(1, io_threads)) as ex:
-            list(ex.map(load, range(len(mine))))
+            # the logits stream into the batch buffer (readinto releases the GIL) while this
+            # thread parses the transcripts
+            loads = [ex.submit(load, n) for n in range(len(mine))]
+            if labs is None:
+                labs = {i: np.asarray(read_transcript_labels(todo[i][1]), dtype=np.int32) for i in mine}
+            for f in loads:
+                f.result()
+        l_off = np.concatenate([[0], np.cumsum([len(labs[i]) for i in mine])]).astype(np.int64)
+        labels = np.concatenate([labs[i] for i in mine]) if mine else np.zeros(0, np.int32)
         t_read = time.perf_counter() - t0
         t0 = time.perf_counter()
         if align_fn is not None:
@@ -382,7 +392,7 @@ def best_path_files(logits_files, voca_files, best_path_files, skip_existing=Tru
         written = [todo[mine[n]][2] for n in good]
         t_write = time.perf_counter() - t0
     if timings is not None:
-        timings.update(read_and_normalise_s=t_read, plan_and_align_s=t_align, write_s=t_write,
+        timings.update(read_normalise_and_labels_s=t_read, plan_and_align_s=t_align, write_s=t_write,
                        total_s=time.perf_counter() - t_start, frames=int(sum(T_all[i] for i in mine)),
                        chapters=len(mine))
     if world > 1:

@@ -11,7 +11,8 @@ _INDEX = {tok: n for n, tok in enumerate(VOCAB)}
 
 
 def encode_text(text):
-    ids = [_INDEX[tok] for tok in text.split() if tok in _INDEX]
+    get = _INDEX.get
+    ids = [i for i in map(get, text.split()) if i is not None]
     return np.array(ids, dtype=np.int8)
 
 
