@@ -132,6 +132,13 @@ int kab_ctc_best_path(const float *log_probs, int64_t T, int32_t vocab_size, con
                       int32_t *best_labels, float *best_scores, float *final_score,
                       int32_t *status);
 
+/*
+ * Device memory of destroyed plans is kept in a per-device pool and reused by later plans (the
+ * drop-in ctc_best_path() builds one plan per call; cudaFree synchronises the device).  This
+ * returns every cached block to the driver.
+ */
+int kab_pool_trim(void);
+
 /* Pinned host memory for kab_plan_run_host callers (cudaHostAlloc / cudaFreeHost). */
 int kab_host_alloc(void **ptr, size_t bytes);
 int kab_host_free(void *ptr);

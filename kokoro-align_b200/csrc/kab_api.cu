@@ -6,6 +6,10 @@
 #include "../../include/kokoro_align_b200.h"
 
 #include <algorithm>
+#include <chrono>
+#include <map>
+#include <mutex>
+#include <unordered_map>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -35,6 +39,106 @@ int cuda_fail(cudaError_t e, const char *what) {
     cudaError_t e_ = (call);                              \
     if (e_ != cudaSuccess) return cuda_fail(e_, #call);   \
   } while (0)
+
+// ---- device memory pool.  The drop-in call ctc_best_path() builds and destroys a plan per
+// lattice, as the reference's per-chapter loop does (run_example.py:247-254): a dozen cudaMalloc /
+// cudaFree pairs per call, and every cudaFree synchronises the device.  Freed blocks are kept per
+// device (size classes of <= 12.5 % slack) and handed out again; kab_pool_trim() returns them to
+// the driver, and the pool trims itself beyond POOL_CAP_BYTES per device.
+constexpr int POOL_MAX_DEV = 64;
+constexpr size_t POOL_CAP_BYTES = (size_t)16 << 30;
+struct DevPool {
+  std::mutex mu;
+  std::multimap<size_t, void *> free_blocks[POOL_MAX_DEV];
+  std::unordered_map<void *, std::pair<size_t, int>> live;  // block -> (class size, device)
+  size_t cached[POOL_MAX_DEV] = {};
+};
+DevPool &pool() {
+  static DevPool *p = new DevPool();  // never destroyed: plans may be freed during interpreter exit
+  return *p;
+}
+size_t pool_class(size_t bytes) {
+  if (bytes < 256) return 256;
+  int lg = 63 - __builtin_clzll((unsigned long long)bytes);
+  const size_t step = std::max<size_t>(256, (size_t)1 << (lg > 3 ? lg - 3 : 0));
+  return (bytes + step - 1) / step * step;
+}
+void pool_trim_device(DevPool &P, int dev, size_t keep_bytes) {  // P.mu held
+  int cur = 0;
+  cudaGetDevice(&cur);
+  bool switched = false;
+  while (P.cached[dev] > keep_bytes && !P.free_blocks[dev].empty()) {
+    auto it = std::prev(P.free_blocks[dev].end());  // largest first
+    if (!switched && cur != dev) { cudaSetDevice(dev); switched = true; }
+    cudaFree(it->second);
+    P.cached[dev] -= it->first;
+    P.free_blocks[dev].erase(it);
+  }
+  if (switched) cudaSetDevice(cur);
+}
+cudaError_t pool_malloc(void **out, size_t bytes) {  // on the current device
+  *out = nullptr;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const size_t cls = pool_class(bytes);
+  DevPool &P = pool();
+  std::lock_guard<std::mutex> lk(P.mu);
+  if (dev < POOL_MAX_DEV) {
+    auto it = P.free_blocks[dev].lower_bound(cls);
+    if (it != P.free_blocks[dev].end() && it->first == cls) {
+      *out = it->second;
+      P.cached[dev] -= cls;
+      P.free_blocks[dev].erase(it);
+      P.live[*out] = {cls, dev};
+      return cudaSuccess;
+    }
+  }
+  e = cudaMalloc(out, cls);
+  if (e != cudaSuccess && dev < POOL_MAX_DEV && P.cached[dev]) {  // out of memory: give the cache back, retry
+    cudaGetLastError();
+    pool_trim_device(P, dev, 0);
+    e = cudaMalloc(out, cls);
+  }
+  if (e == cudaSuccess) P.live[*out] = {cls, dev};
+  return e;
+}
+void pool_free(void *ptr) {
+  if (!ptr) return;
+  DevPool &P = pool();
+  std::lock_guard<std::mutex> lk(P.mu);
+  auto it = P.live.find(ptr);
+  if (it == P.live.end()) { cudaFree(ptr); return; }
+  const size_t cls = it->second.first;
+  const int dev = it->second.second;
+  P.live.erase(it);
+  if (dev >= POOL_MAX_DEV) { cudaFree(ptr); return; }
+  P.free_blocks[dev].emplace(cls, ptr);
+  P.cached[dev] += cls;
+  if (P.cached[dev] > POOL_CAP_BYTES) pool_trim_device(P, dev, POOL_CAP_BYTES / 2);
+}
+int sm_count_of(int device, int *out) {  // (cudaGetDeviceProperties takes milliseconds; this is cached)
+  static int cache[POOL_MAX_DEV] = {};
+  if (device >= 0 && device < POOL_MAX_DEV && cache[device]) { *out = cache[device]; return KAB_OK; }
+  int n = 0;
+  KAB_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device));
+  if (device >= 0 && device < POOL_MAX_DEV) cache[device] = n;
+  *out = n;
+  return KAB_OK;
+}
+// KAB_TRACE=1: wall time of the host-side phases of every call, to stderr (development)
+struct Trace {
+  bool on;
+  const char *what;
+  std::chrono::steady_clock::time_point t0;
+  explicit Trace(const char *w) : on(getenv("KAB_TRACE") != nullptr), what(w), t0(std::chrono::steady_clock::now()) {}
+  void mark(const char *phase) {
+    if (!on) return;
+    const auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[kab] %s: %s %.3f ms\n", what, phase, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
 
 // kernel classes (one work queue each)
 constexpr int N_QUEUES = 4;
@@ -117,12 +221,16 @@ namespace {
 
 int plan_free(kab_plan *pl) {
   if (!pl) return KAB_OK;
+  Trace tr("kab_plan_destroy");
   cudaSetDevice(pl->device);
-  for (int q = 0; q < N_QUEUES; ++q) cudaFree(pl->d_lists[q]);
-  cudaFree(pl->d_col16); cudaFree(pl->d_raw); cudaFree(pl->d_bp); cudaFree(pl->d_scratch);
-  cudaFree(pl->d_queue); cudaFree(pl->d_status_init); cudaFree(pl->d_wide_ws); cudaFree(pl->d_band_fifo); cudaFree(pl->d_bt_meta); cudaFree(pl->d_bt_maps); cudaFree(pl->d_bt_entry); cudaFree(pl->d_end_state); cudaFree(pl->d_gather); cudaFree(pl->d_lpc);
-  cudaFree(pl->d_lp); cudaFree(pl->d_path); cudaFree(pl->d_lab); cudaFree(pl->d_st);
-  cudaFree(pl->d_sc); cudaFree(pl->d_fs);
+  // pooled blocks may be handed to another plan at once, so nothing of this one may still be in
+  // flight on any stream (kab_plan_run_device is asynchronous); cudaFree used to imply the same wait
+  if (!pl->is_child) cudaDeviceSynchronize();
+  for (int q = 0; q < N_QUEUES; ++q) pool_free(pl->d_lists[q]);
+  pool_free(pl->d_col16); pool_free(pl->d_raw); pool_free(pl->d_bp); pool_free(pl->d_scratch);
+  pool_free(pl->d_queue); pool_free(pl->d_status_init); pool_free(pl->d_wide_ws); pool_free(pl->d_band_fifo); pool_free(pl->d_bt_meta); pool_free(pl->d_bt_maps); pool_free(pl->d_bt_entry); pool_free(pl->d_end_state); pool_free(pl->d_gather); pool_free(pl->d_lpc);
+  pool_free(pl->d_lp); pool_free(pl->d_path); pool_free(pl->d_lab); pool_free(pl->d_st);
+  pool_free(pl->d_sc); pool_free(pl->d_fs);
   if (pl->stream) cudaStreamDestroy(pl->stream);
   if (pl->s_in) cudaStreamDestroy(pl->s_in);
   if (pl->s_out) cudaStreamDestroy(pl->s_out);
@@ -130,6 +238,7 @@ int plan_free(kab_plan *pl) {
   for (cudaEvent_t e : pl->ev_cmp) cudaEventDestroy(e);
   for (kab_plan *c : pl->segs) plan_free(c);
   delete pl;
+  tr.mark("free");
   return KAB_OK;
 }
 
@@ -178,10 +287,8 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
     pl->h_l_off.assign(l_off, l_off + B + 1);
     if (pl->total_L > 0) pl->h_labels.assign(labels, labels + pl->total_L);
   }
-  cudaDeviceProp prop;
-  cudaError_t ce = cudaGetDeviceProperties(&prop, device);
-  if (ce != cudaSuccess) { delete pl; return cuda_fail(ce, "cudaGetDeviceProperties"); }
-  pl->sm_count = prop.multiProcessorCount;
+  Trace tr("kab_plan_create");
+  if (int rcs = sm_count_of(device, &pl->sm_count)) { delete pl; return rcs; }
 
   // ---- wide vocabularies: can the staged kernels work on a compact copy of the log-probs?
   // (every lattice they would take uses at most MAX_STAGE_V - 1 distinct label columns)
@@ -388,11 +495,12 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
     }
   }
 
+  tr.mark("classify");
   // ---- device allocations
   int rc = KAB_OK;
   auto up = [&](void **dst, const void *src, size_t bytes) -> int {
     if (!bytes) return KAB_OK;
-    KAB_CUDA(cudaMalloc(dst, bytes));
+    KAB_CUDA(pool_malloc(dst, bytes));
     KAB_CUDA(cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
     return KAB_OK;
   };
@@ -403,17 +511,17 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
     if ((rc = up((void **)&pl->d_col16, col16.data(), col16.size() * sizeof(uint16_t)))) break;
     if (pl->Vc) {
       if ((rc = up((void **)&pl->d_gather, h_gather.data(), h_gather.size() * sizeof(int32_t)))) break;
-      cudaError_t e2 = cudaMalloc((void **)&pl->d_lpc, (size_t)pl->total_T * pl->Vc * sizeof(float));
-      if (e2 != cudaSuccess) { rc = cuda_fail(e2, "cudaMalloc(compact log-probs)"); break; }
+      cudaError_t e2 = pool_malloc((void **)&pl->d_lpc, (size_t)pl->total_T * pl->Vc * sizeof(float));
+      if (e2 != cudaSuccess) { rc = cuda_fail(e2, "pool_malloc(compact log-probs)"); break; }
     }
     if (!pl->lists[Q_GENERIC].empty())
       if ((rc = up((void **)&pl->d_raw, labels, (size_t)pl->total_L * sizeof(int32_t)))) break;
     if (pl->any_bad_label)
       if ((rc = up((void **)&pl->d_status_init, status_init.data(), (size_t)B * sizeof(int32_t)))) break;
     cudaError_t e;
-    if (bp_bytes && (e = cudaMalloc((void **)&pl->d_bp, (size_t)bp_bytes)) != cudaSuccess) { rc = cuda_fail(e, "cudaMalloc(backpointers)"); break; }
-    if (scr_floats && (e = cudaMalloc((void **)&pl->d_scratch, (size_t)scr_floats * 4)) != cudaSuccess) { rc = cuda_fail(e, "cudaMalloc(scratch)"); break; }
-    if ((e = cudaMalloc((void **)&pl->d_queue, N_QUEUES * sizeof(unsigned int))) != cudaSuccess) { rc = cuda_fail(e, "cudaMalloc(queue)"); break; }
+    if (bp_bytes && (e = pool_malloc((void **)&pl->d_bp, (size_t)bp_bytes)) != cudaSuccess) { rc = cuda_fail(e, "pool_malloc(backpointers)"); break; }
+    if (scr_floats && (e = pool_malloc((void **)&pl->d_scratch, (size_t)scr_floats * 4)) != cudaSuccess) { rc = cuda_fail(e, "pool_malloc(scratch)"); break; }
+    if ((e = pool_malloc((void **)&pl->d_queue, N_QUEUES * sizeof(unsigned int))) != cudaSuccess) { rc = cuda_fail(e, "pool_malloc(queue)"); break; }
 
     // ---- launch geometry
     if (!pl->lists[Q_WARP].empty()) {
@@ -433,12 +541,12 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
     }
     if (!pl->bt_meta.empty()) {
       if ((rc = up((void **)&pl->d_bt_meta, pl->bt_meta.data(), pl->bt_meta.size() * sizeof(KabBtMeta)))) break;
-      if ((e = cudaMalloc((void **)&pl->d_bt_maps, (size_t)pl->bt_map_ints * 4)) != cudaSuccess) { rc = cuda_fail(e, "cudaMalloc(backtrack maps)"); break; }
-      if ((e = cudaMalloc((void **)&pl->d_bt_entry, (size_t)pl->bt_blocks * 4)) != cudaSuccess) { rc = cuda_fail(e, "cudaMalloc(backtrack entries)"); break; }
-      if ((e = cudaMalloc((void **)&pl->d_end_state, (size_t)pl->B * 4)) != cudaSuccess) { rc = cuda_fail(e, "cudaMalloc(end states)"); break; }
+      if ((e = pool_malloc((void **)&pl->d_bt_maps, (size_t)pl->bt_map_ints * 4)) != cudaSuccess) { rc = cuda_fail(e, "pool_malloc(backtrack maps)"); break; }
+      if ((e = pool_malloc((void **)&pl->d_bt_entry, (size_t)pl->bt_blocks * 4)) != cudaSuccess) { rc = cuda_fail(e, "pool_malloc(backtrack entries)"); break; }
+      if ((e = pool_malloc((void **)&pl->d_end_state, (size_t)pl->B * 4)) != cudaSuccess) { rc = cuda_fail(e, "pool_malloc(end states)"); break; }
     }
     if (!pl->lists[Q_BAND].empty() && pl->band_nc > 0) {
-      if ((e = cudaMalloc((void **)&pl->d_band_fifo, (size_t)pl->band_fifo_bytes)) != cudaSuccess) { rc = cuda_fail(e, "cudaMalloc(band FIFOs)"); break; }
+      if ((e = pool_malloc((void **)&pl->d_band_fifo, (size_t)pl->band_fifo_bytes)) != cudaSuccess) { rc = cuda_fail(e, "pool_malloc(band FIFOs)"); break; }
       const KabBandpGeom geo = kab_bandp_geom(pl->stage_bytes);
       if ((e = cudaFuncSetAttribute(kab_bandp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)geo.smem_bytes)) != cudaSuccess) { rc = cuda_fail(e, "cudaFuncSetAttribute(bandp)"); break; }
       pl->smem[Q_BAND] = geo.smem_bytes;
@@ -464,13 +572,14 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
       pl->grid[Q_BAND] = (int)std::min<int64_t>((int64_t)pl->lists[Q_BAND].size(), (int64_t)pl->sm_count * std::max(occ, 1));
     }
     if (!pl->lists[Q_WIDE].empty()) {
-      if ((e = cudaMalloc((void **)&pl->d_wide_ws, (size_t)pl->wide_ws_bytes)) != cudaSuccess) { rc = cuda_fail(e, "cudaMalloc(wide workspace)"); break; }
+      if ((e = pool_malloc((void **)&pl->d_wide_ws, (size_t)pl->wide_ws_bytes)) != cudaSuccess) { rc = cuda_fail(e, "pool_malloc(wide workspace)"); break; }
       pl->smem[Q_WIDE] = kab_wide_geom(pl->stage_bytes).smem_bytes;
       pl->grid[Q_WIDE] = wide_max_ctas + 1;  // forward CTAs + the backtrack CTA
     }
     if (!pl->lists[Q_GENERIC].empty())
       pl->grid[Q_GENERIC] = (int)std::min<int64_t>((int64_t)pl->lists[Q_GENERIC].size(), (int64_t)pl->sm_count * 4);
   } while (0);
+  tr.mark("allocate, upload, kernel attributes");
   if (rc != KAB_OK) { plan_free(pl); return rc; }
 
   info.backptr_bytes = bp_bytes;
@@ -708,18 +817,19 @@ static int run_host_impl(kab_plan *pl, const float *h_log_probs, int32_t *h_best
   if (pl->B == 0) return KAB_OK;
   if (!h_log_probs || !h_best_path || !h_best_labels || !h_best_scores || !h_status) return KAB_E_BAD_ARG;
   KAB_CUDA(cudaSetDevice(pl->device));
+  Trace tr("kab_plan_run_host");
   const size_t n = (size_t)pl->total_T, B = (size_t)pl->B;
   const int64_t V = pl->V;
   if (!pl->stream) {
     KAB_CUDA(cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking));
     KAB_CUDA(cudaStreamCreateWithFlags(&pl->s_in, cudaStreamNonBlocking));
     KAB_CUDA(cudaStreamCreateWithFlags(&pl->s_out, cudaStreamNonBlocking));
-    KAB_CUDA(cudaMalloc((void **)&pl->d_lp, n * V * 4));
-    KAB_CUDA(cudaMalloc((void **)&pl->d_path, n * 4));
-    KAB_CUDA(cudaMalloc((void **)&pl->d_lab, n * 4));
-    KAB_CUDA(cudaMalloc((void **)&pl->d_sc, n * 4));
-    KAB_CUDA(cudaMalloc((void **)&pl->d_fs, B * 4));
-    KAB_CUDA(cudaMalloc((void **)&pl->d_st, B * 4));
+    KAB_CUDA(pool_malloc((void **)&pl->d_lp, n * V * 4));
+    KAB_CUDA(pool_malloc((void **)&pl->d_path, n * 4));
+    KAB_CUDA(pool_malloc((void **)&pl->d_lab, n * 4));
+    KAB_CUDA(pool_malloc((void **)&pl->d_sc, n * 4));
+    KAB_CUDA(pool_malloc((void **)&pl->d_fs, B * 4));
+    KAB_CUDA(pool_malloc((void **)&pl->d_st, B * 4));
     // ---- cut the batch into segments of >= 32 MB of log-probs, at lattice boundaries whose
     // first row is 16-byte aligned (bulk copies), at most 12 segments
     const int64_t bytes_total = (int64_t)n * V * 4;
@@ -759,6 +869,7 @@ static int run_host_impl(kab_plan *pl, const float *h_log_probs, int32_t *h_best
       }
     }
   }
+  tr.mark("streams, buffers, segments");
   if (pl->segs.empty()) {  // small batch: one copy in, one run, one copy out
     cudaStream_t s = pl->stream;
     KAB_CUDA(cudaMemcpyAsync(pl->d_lp, h_log_probs, n * V * 4, cudaMemcpyHostToDevice, s));
@@ -772,7 +883,9 @@ static int run_host_impl(kab_plan *pl, const float *h_log_probs, int32_t *h_best
     KAB_CUDA(cudaMemcpyAsync(h_best_scores, pl->d_sc, n * 4, cudaMemcpyDeviceToHost, s));
     if (h_final_score) KAB_CUDA(cudaMemcpyAsync(h_final_score, pl->d_fs, B * 4, cudaMemcpyDeviceToHost, s));
     KAB_CUDA(cudaMemcpyAsync(h_status, pl->d_st, B * 4, cudaMemcpyDeviceToHost, s));
+    tr.mark("enqueue");
     KAB_CUDA(cudaStreamSynchronize(s));
+    tr.mark("synchronize");
     return KAB_OK;
   }
   // ---- pipelined: three streams (copy in / kernels / copy out), one event pair per segment
@@ -830,6 +943,13 @@ int kab_ctc_best_path(const float *log_probs, int64_t T, int32_t V, const int32_
   rc = kab_plan_run_host(pl, log_probs, best_path, best_labels, best_scores, final_score, status);
   kab_plan_destroy(pl);
   return rc;
+}
+
+int kab_pool_trim(void) {
+  DevPool &P = pool();
+  std::lock_guard<std::mutex> lk(P.mu);
+  for (int d = 0; d < POOL_MAX_DEV; ++d) pool_trim_device(P, d, 0);
+  return KAB_OK;
 }
 
 int kab_host_alloc(void **ptr, size_t bytes) {

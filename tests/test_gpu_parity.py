@@ -323,3 +323,28 @@ def test_wide_unbanded_lattices(kab, T, L):
     beam = 2 * (2 * int(Ls.max()) + 1) + 2
     info = _compare_batch(kab, lp, t_off, labels, l_off, beam_size=beam)
     assert info.n_class[3] >= 2 and info.n_class[2] == 0
+
+
+def test_memory_pool_reuse_and_trim(kab):
+    """Plans built one after the other reuse the device blocks of destroyed ones (dirty memory:
+    nothing may rely on zero-filled allocations), kab_pool_trim() returns the cache to the driver,
+    and a plan destroyed right after an ASYNCHRONOUS run does not hand its workspace to the next
+    plan while its kernels are still in flight."""
+    import torch
+    from kokoro_align_b200 import _lib, synth
+    from oracle import ctc_oracle
+    shapes = [(5000, 700), (300, 42), (5000, 700), (9000, 1260), (300, 42), (5000, 700)]
+    outs = []
+    for k, (T, L) in enumerate(shapes):
+        lp, labels = synth.make_lattice(T, L, 39, seed=8800 + k)
+        plan = kab.AlignPlan([0, T], labels, [0, L], 39)
+        outs.append((plan.run_torch(torch.from_numpy(lp).cuda()), lp, labels))
+        plan.close()                                   # asynchronous work may still be running
+        if k == 3:
+            assert _lib.lib().kab_pool_trim() == 0
+    torch.cuda.synchronize()
+    for (path, labs, scores, final, status), lp, labels in outs:
+        rp, rl, rs, rf = ctc_oracle.ctc_best_path(lp, labels, return_final_score=True)
+        assert int(status[0]) == 0
+        np.testing.assert_array_equal(path.cpu().numpy(), rp)
+        assert scores.cpu().numpy().tobytes() == rs.tobytes()
