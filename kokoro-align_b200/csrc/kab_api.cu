@@ -587,7 +587,7 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
                          (pl->d_raw ? pl->total_L * 4 : 0) + B * (int64_t)sizeof(KabLattice);
   info.kernel_launches = 0;
   for (int q = 0; q < N_QUEUES; ++q) info.kernel_launches += pl->lists[q].empty() ? 0 : 1;
-  if (!pl->bt_meta.empty()) info.kernel_launches += 2;  // kab_bt_maps_kernel, kab_bt_stitch_kernel
+  if (!pl->bt_meta.empty()) info.kernel_launches += 3;  // kab_bt_maps_kernel, kab_bt_stitch_kernel, kab_bt_gather_kernel
   if (pl->Vc)                                          // kab_compact_kernel, kab_expand_labels_kernel
     for (int q : {Q_WARP, Q_BAND, Q_WIDE}) info.kernel_launches += pl->lists[q].empty() ? 0 : 2;
   *out = pl;
@@ -700,6 +700,8 @@ int kab_plan_run_device(kab_plan *pl, const float *d_log_probs, int32_t *d_best_
                                                               d_status, pl->d_bt_maps, pl->W, nwt);
         kab_bt_stitch_kernel<<<n_band, 1024, 0, stream>>>(pl->d_lists[Q_BAND], pl->d_bt_meta, pb, pl->d_end_state,
                                                           pl->d_bt_maps, pl->d_bt_entry, nwt);
+        const dim3 gg((unsigned)n_band, (unsigned)((pl->max_T[Q_BAND] + KAB_BT_GATHER_FRAMES - 1) / KAB_BT_GATHER_FRAMES));
+        kab_bt_gather_kernel<<<gg, 256, 0, stream>>>(pl->d_lists[Q_BAND], pb);
       }
     } else if (pl->band_nw <= 16)
       kab_band_kernel<512><<<pl->grid[Q_BAND], pl->band_nw * 32, pl->smem[Q_BAND], stream>>>(

@@ -6,7 +6,7 @@
 // long lattice, on ONE thread, while the rest of the GPU idles (a plan that uses this kernel has
 // at most a few dozen lattices).  The steps are function compositions, so they parallelise
 // exactly -- no speculation:
-//   1. kab_bt_maps_kernel: the frames are cut into blocks of KAB_BT_BLOCK.  For every block and
+//   1. kab_bt_maps_kernel: the frames are cut into blocks of KAB_BT_BLOCK frames.  For every block and
 //      EVERY state of the window at the block's last frame, one thread walks the block backwards
 //      and records where it leaves it: maps[block][v - lo] = state at the frame before the block.
 //      T x W steps in total (as many as the forward pass has cells), spread over the whole GPU.
@@ -15,7 +15,9 @@
 //   2. kab_bt_stitch_kernel (one CTA per lattice): thread 0 composes the maps from the forced end
 //      state down -- T / KAB_BT_BLOCK dependent table look-ups -- which yields the true entry
 //      state of every block; then the threads re-walk the blocks from their entry states, all
-//      blocks at once, and write best_path / best_labels / best_scores (align.py:105-107).
+//      blocks at once (best_path);
+//   3. kab_bt_gather_kernel: best_labels and best_scores of the path (align.py:105-107), coalesced
+//      over the frames.
 // Backpointer layout (written by kab_bandp_kernel): byte of (frame t, state v) at
 //     bp[((reg * n_groups + t / 8) * 32 + col) * 8 + t % 8],   slot = v mod R, reg = slot / 104,
 //     col = (slot % 104) / 4, move = (byte >> 2 * (slot & 3)) & 3.
@@ -23,7 +25,7 @@
 #include "kab_band.cuh"
 #include "kab_common.cuh"
 
-#define KAB_BT_BLOCK 512    // frames per block
+#define KAB_BT_BLOCK 1024   // frames per block
 #define KAB_BT_THREADS 128  // threads per CTA of the map kernel (= entry states per CTA)
 
 struct KabBtMeta {       // one per lattice of the band list (same order)
@@ -34,30 +36,46 @@ struct KabBtMeta {       // one per lattice of the band list (same order)
   int32_t pad;
 };
 
-// walker state: state v, its position rs inside ring region reg, that region's backpointer rows
+// walker: state v, its position rs inside ring region reg, and gp = the backpointer rows of that
+// region for the CURRENT 8-frame group (the caller moves it down by 256 bytes per group)
 struct KabBtWalker {
   int v, rs, reg;
-  const unsigned char *rows;  // bp + reg * n_groups * 256
-  __device__ __forceinline__ void init(int v0, int R, const unsigned char *bp, int n_groups) {
+  const unsigned char *gp;
+  __device__ __forceinline__ void init(int v0, int R, const unsigned char *bp, int64_t stride, int g) {
     v = v0;
     const int slot = v0 % R;
     reg = slot / KAB_BAND_OW;
     rs = slot - reg * KAB_BAND_OW;
-    rows = bp + (size_t)reg * n_groups * 256;
+    gp = bp + reg * stride + (size_t)g * 256;
   }
-  // one frame back; returns the state AT frame t (before the move)
-  __device__ __forceinline__ int step(int t, int NWT, const unsigned char *bp, int n_groups) {
-    const unsigned int byte = rows[(size_t)(t >> 3) * 256 + (rs >> 2) * 8 + (t & 7)];
+  // one frame back (frame f of the current group); returns the state AT that frame (before the move)
+  __device__ __forceinline__ int step(int f, int NWT, int64_t stride) {
+    const unsigned int byte = gp[((rs >> 2) << 3) + f];
     const int at = v;
     const int mv = min((int)((byte >> (2 * (rs & 3))) & 3u), v);  // (clamp: only garbage walkers hit it)
     v -= mv;
     rs -= mv;
     if (rs < 0) {  // into the region below (a move crosses at most one boundary)
       rs += KAB_BAND_OW;
-      reg = reg == 0 ? NWT - 1 : reg - 1;
-      rows = bp + (size_t)reg * n_groups * 256;
+      const bool wrap = reg == 0;
+      reg = wrap ? NWT - 1 : reg - 1;
+      gp += wrap ? (int64_t)(NWT - 1) * stride : -stride;
     }
     return at;
+  }
+  // frames te .. t0 (t0 a multiple of 8), descending; f(t, state at t) for every frame
+  template <class F>
+  __device__ __forceinline__ void walk(int te, int t0, int NWT, int64_t stride, F f) {
+    int g = te >> 3;
+    if ((te & 7) != 7) {  // partial group at the top (the last frames of the lattice)
+      for (int k = te & 7; k >= 0; --k) f(g * 8 + k, step(k, NWT, stride));
+      --g;
+      gp -= 256;
+    }
+    for (; g >= (t0 >> 3); --g, gp -= 256) {
+#pragma unroll
+      for (int k = 7; k >= 0; --k) f(g * 8 + k, step(k, NWT, stride));
+    }
   }
 };
 
@@ -83,9 +101,10 @@ kab_bt_maps_kernel(const KabLattice *__restrict__ lats, const KabBtMeta *__restr
   const int j = blockIdx.y * KAB_BT_THREADS + threadIdx.x;
   if (lo + j >= hi) return;
   const unsigned char *bp = bpw + lat.bp_off;
+  const int64_t stride = (int64_t)n_groups * 256;
   KabBtWalker w;
-  w.init(lo + j, R, bp, n_groups);
-  for (int t = te; t >= t0; --t) w.step(t, NWT, bp, n_groups);
+  w.init(lo + j, R, bp, stride, te >> 3);
+  w.walk(te, t0, NWT, stride, [](int, int) {});
   maps[m.map_off + (int64_t)b * m.wl + j] = w.v;
 }
 
@@ -97,33 +116,51 @@ kab_bt_stitch_kernel(const KabLattice *__restrict__ lats, const KabBtMeta *__res
   const KabLattice lat = lats[blockIdx.x];
   const KabBtMeta m = meta[blockIdx.x];
   if (p.status[lat.index] != 0) return;
-  const int T = lat.T, S = 2 * lat.L + 1, W = p.W, V = p.V, R = KAB_BAND_OW * NWT, n_groups = (T + 7) / 8;
+  const int T = lat.T, S = 2 * lat.L + 1, W = p.W, R = KAB_BAND_OW * NWT, n_groups = (T + 7) / 8;
   int32_t *ent = entry + m.first_block;
-  if (threadIdx.x == 0) {  // compose the block maps from the forced end state down
+  // window start of every block's last frame (64-bit divisions): all threads, off the chain below
+  for (int b = threadIdx.x; b < m.n_blocks; b += blockDim.x)
+    ent[b] = kab_bt_lo(S, min(T, (b + 1) * KAB_BT_BLOCK) - 1, T, W);
+  __syncthreads();
+  if (threadIdx.x == 0) {  // compose the block maps from the forced end state down: one L2 load per block
     int v = end_state[lat.index];
     for (int b = m.n_blocks - 1; b >= 0; --b) {
+      const int lo = ent[b];
       ent[b] = v;
-      const int te = min(T, (b + 1) * KAB_BT_BLOCK) - 1;
-      v = __ldcg(&maps[m.map_off + (int64_t)b * m.wl + (v - kab_bt_lo(S, te, T, W))]);
+      v = __ldcg(&maps[m.map_off + (int64_t)b * m.wl + (v - lo)]);
     }
   }
   __syncthreads();
+  // every block re-walked from its entry state, one thread each: only the backpointer bytes are on
+  // the dependent chain (eight frames share a sector)
   const unsigned char *bp = p.bp + lat.bp_off;
-  const uint16_t *col16 = p.col16 + lat.col_off;
+  const int64_t stride = (int64_t)n_groups * 256;
   int32_t *out_path = p.best_path + lat.t_off;
-  int32_t *out_lab = p.best_labels + lat.t_off;
-  float *out_sc = p.best_scores + lat.t_off;
-  const float *lp = p.lp + lat.t_off * (int64_t)V;
   for (int b = threadIdx.x; b < m.n_blocks; b += blockDim.x) {
     const int t0 = b * KAB_BT_BLOCK, te = min(T, t0 + KAB_BT_BLOCK) - 1;
     KabBtWalker w;
-    w.init(ent[b], R, bp, n_groups);
-    for (int t = te; t >= t0; --t) {
-      const int pv = w.step(t, NWT, bp, n_groups);
-      const int lab = (pv & 1) ? (int)col16[(pv - 1) >> 1] : 0;
-      out_path[t] = pv;
-      out_lab[t] = lab;                              // align.py:106
-      out_sc[t] = __ldg(&lp[(int64_t)t * V + lab]);  // align.py:107
-    }
+    w.init(ent[b], R, bp, stride, te >> 3);
+    w.walk(te, t0, NWT, stride, [&](int t, int at) { out_path[t] = at; });
+  }
+}
+
+// labels and scores of the path (align.py:105-107): grid (lattices, chunks of 4096 frames), coalesced
+#define KAB_BT_GATHER_FRAMES 4096
+__global__ void __launch_bounds__(256)
+kab_bt_gather_kernel(const KabLattice *__restrict__ lats, KabParams p) {
+  const KabLattice lat = lats[blockIdx.x];
+  const int f0 = blockIdx.y * KAB_BT_GATHER_FRAMES;
+  if (f0 >= lat.T || p.status[lat.index] != 0) return;
+  const int f1 = min(lat.T, f0 + KAB_BT_GATHER_FRAMES), V = p.V;
+  const uint16_t *col16 = p.col16 + lat.col_off;
+  const int32_t *path = p.best_path + lat.t_off;
+  int32_t *out_lab = p.best_labels + lat.t_off;
+  float *out_sc = p.best_scores + lat.t_off;
+  const float *lp = p.lp + lat.t_off * (int64_t)V;
+  for (int t = f0 + threadIdx.x; t < f1; t += blockDim.x) {
+    const int pv = path[t];
+    const int lab = (pv & 1) ? (int)col16[(pv - 1) >> 1] : 0;
+    out_lab[t] = lab;                              // align.py:106
+    out_sc[t] = __ldg(&lp[(int64_t)t * V + lab]);  // align.py:107
   }
 }
