@@ -152,6 +152,11 @@ def ctc_best_path(log_probs, labels, beam_size=1000, max_move=4, return_final_sc
     return path, labs, scores
 
 
+def trim_pool():
+    """Return the device memory cached from destroyed plans to the driver (kab_pool_trim)."""
+    _lib.check(_lib.lib().kab_pool_trim())
+
+
 def _current_device():
     try:
         import torch
