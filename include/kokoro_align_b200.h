@@ -133,6 +133,18 @@ int kab_ctc_best_path(const float *log_probs, int64_t T, int32_t vocab_size, con
                       int32_t *status);
 
 /*
+ * Labels of a `text|voca` transcript file, transcript.py:60-67 + encoder.py:5-19: the second
+ * '|'-separated field of every line, split at spaces, tokens looked up in the vocabulary and
+ * unknown ones dropped.  `text` = the file's bytes; token_ids[b0 | b1 << 8] = id of the 1- or
+ * 2-byte token (b1 = 0 for one byte) or -1; `labels` needs room for n_bytes / 2 + 1 ids.
+ * Host-only (no CUDA).  Returns KAB_E_UNSUPPORTED when the bytes leave the plain case the
+ * byte-level scan reproduces exactly (a line without '|', a lone '\r', control or non-ASCII
+ * bytes inside a voca field); the Python caller then runs the reference's own text code.
+ */
+int kab_encode_transcript(const uint8_t *text, int64_t n_bytes, const int16_t *token_ids,
+                          int8_t *labels, int64_t *n_labels);
+
+/*
  * Device memory of destroyed plans is kept in a per-device pool and reused by later plans (the
  * drop-in ctc_best_path() builds one plan per call; cudaFree synchronises the device).  This
  * returns every cached block to the driver.

@@ -190,9 +190,8 @@ def log_softmax_torch(logits, out=None, stream=None):
     return out
 
 
-def read_transcript_labels(voca_file):
-    """Labels of a ``text|voca`` transcript: transcript.py:60-67 + encoder.py:5-19 (tokens
-    outside the 39-symbol vocabulary are dropped, int8 ids)."""
+def _read_transcript_labels_text(voca_file):
+    """transcript.py:60-67 + encoder.py:18-19, line by line (the reference's own control flow)."""
     from .encoder import encode_text
     res = []
     with open(voca_file) as f:
@@ -200,6 +199,35 @@ def read_transcript_labels(voca_file):
             parts = line.rstrip('\r\n').split('|')
             res.append(parts[1])
     return encode_text(' '.join(res))
+
+
+_TOKEN_IDS = None
+
+
+def read_transcript_labels(voca_file):
+    """Labels of a ``text|voca`` transcript: transcript.py:60-67 + encoder.py:5-19 (tokens
+    outside the 39-symbol vocabulary are dropped, int8 ids).  The plain case (ASCII phonemes
+    separated by spaces) is scanned by kab_encode_transcript in the C library -- a book's
+    transcripts hold ~4e5 tokens and the per-token Python loop was a third of the files-to-files
+    time; anything else takes the reference's own text code path."""
+    global _TOKEN_IDS
+    if _TOKEN_IDS is None:
+        from .encoder import VOCAB
+        table = np.full(65536, -1, np.int16)
+        for n, tok in enumerate(VOCAB):
+            b = tok.encode()
+            assert 1 <= len(b) <= 2
+            table[b[0] | ((b[1] << 8) if len(b) > 1 else 0)] = n
+        _TOKEN_IDS = table
+    with open(voca_file, 'rb') as f:
+        raw = f.read()
+    out = np.empty(len(raw) // 2 + 1, np.int8)
+    n = ctypes.c_int64(0)
+    rc = _lib.lib().kab_encode_transcript(raw, len(raw), _ptr(_TOKEN_IDS), _ptr(out), ctypes.byref(n))
+    if rc == _lib.KAB_E_UNSUPPORTED:
+        return _read_transcript_labels_text(voca_file)
+    _lib.check(rc)
+    return out[:n.value].copy()
 
 
 def best_path(input_file, voca_file, output_file, device_log_softmax=False):
@@ -301,7 +329,7 @@ class _PinnedPool:
 
 def best_path_files(logits_files, voca_files, best_path_files, skip_existing=True, beam_size=1000,
                     max_move=4, verbose=True, device_log_softmax=False, io_threads=8, timings=None,
-                    align_fn=None):
+                    align_fn=None, pipeline=True):
     """The per-book loop of run_example.py:247-254 as ONE batch: every chapter whose output does
     not exist yet is read straight into one pinned batch buffer (npz_read_into), normalised
     (align.py:116-117: numpy on the host by default -- bit-identical to the reference -- or on the
@@ -314,7 +342,8 @@ def best_path_files(logits_files, voca_files, best_path_files, skip_existing=Tru
     Under torch.distributed (one process per GPU) every rank reads and aligns its own LPT shard
     of the chapters (parallel.shard_batch: no collective on the data path) and writes its own
     output files; the written paths are gathered on rank 0 (other ranks return []).
-    ``timings``: optional dict that receives the wall seconds of every phase."""
+    ``timings``: optional dict that receives the wall seconds of every phase (per phase the
+    slower of the two groups).  ``pipeline=False`` aligns all chapters in one plan."""
     import os
     import time
     from concurrent.futures import ThreadPoolExecutor
@@ -348,58 +377,95 @@ def best_path_files(logits_files, voca_files, best_path_files, skip_existing=Tru
     else:
         mine = list(range(len(todo)))
     written, first_bad = [], ST_OK
-    t_read = t_norm = t_align = t_write = 0.0
+    group_times = []
     if mine:
-        t_off = np.concatenate([[0], np.cumsum([T_all[i] for i in mine])]).astype(np.int64)
         if any(T_all[i] == 0 for i in mine):   # beams[-1] on an empty list, align.py:100
             raise IndexError("list index out of range")
+        # Two groups, each with its own plan and host thread: the chapters on the critical path
+        # (at least half as long as the longest) and the rest.  The long group is read, copied and
+        # launched first, so its forward passes -- which bound the book -- start while the many
+        # short chapters are still being read and their transcripts parsed; both plans then run
+        # side by side on the GPU (every chapter lattice has its own cluster of SMs).
+        t_max = max(T_all[i] for i in mine)
+        long_group = [i for i in mine if 2 * T_all[i] >= t_max]
+        short_group = [i for i in mine if 2 * T_all[i] < t_max]
+        groups = [long_group, short_group] if (pipeline and align_fn is None and long_group and short_group
+                                               and len(mine) >= 4) else [mine]
+        rows = int(sum(T_all[i] for i in mine))
         # (align_fn: the multi-rank CPU tests replace the CUDA plan; then no pinned memory either)
-        batch = (_PinnedPool.array((int(t_off[-1]), V)) if align_fn is None
-                 else np.empty((int(t_off[-1]), V), np.float32))
-        t0 = time.perf_counter()
+        batch = _PinnedPool.array((rows, V)) if align_fn is None else np.empty((rows, V), np.float32)
+        device = _current_device()
+        io = ThreadPoolExecutor(max(1, io_threads))
 
-        def load(n):
-            dst = batch[int(t_off[n]):int(t_off[n + 1])]
-            npz_read_into(todo[mine[n]][0], dst, info=infos[mine[n]])
-            if not device_log_softmax:
-                dst[...] = log_softmax(dst)
-        with ThreadPoolExecutor(max(1, io_threads)) as ex:
+        def run_group(members, row0):
+            tm = {}
+            t0 = time.perf_counter()
+            t_off = np.concatenate([[0], np.cumsum([T_all[i] for i in members])]).astype(np.int64)
+            view = batch[row0:row0 + int(t_off[-1])]
+
+            def load(n):
+                dst = view[int(t_off[n]):int(t_off[n + 1])]
+                npz_read_into(todo[members[n]][0], dst, info=infos[members[n]])
+                if not device_log_softmax:
+                    dst[...] = log_softmax(dst)
             # the logits stream into the batch buffer (readinto releases the GIL) while this
             # thread parses the transcripts
-            loads = [ex.submit(load, n) for n in range(len(mine))]
-            if labs is None:
-                labs = {i: np.asarray(read_transcript_labels(todo[i][1]), dtype=np.int32) for i in mine}
+            loads = [io.submit(load, n) for n in range(len(members))]
+            glabs = [labs[i] if labs is not None else
+                     np.asarray(read_transcript_labels(todo[i][1]), dtype=np.int32) for i in members]
             for f in loads:
                 f.result()
-        l_off = np.concatenate([[0], np.cumsum([len(labs[i]) for i in mine])]).astype(np.int64)
-        labels = np.concatenate([labs[i] for i in mine]) if mine else np.zeros(0, np.int32)
-        t_read = time.perf_counter() - t0
-        t0 = time.perf_counter()
-        if align_fn is not None:
-            path, lab, sc, _, status = align_fn(batch, t_off, labels, l_off, V, beam_size, max_move, 0)
-        else:
-            with AlignPlan(t_off, labels, l_off, V, beam_size, max_move, device=_current_device()) as plan:
-                path, lab, sc, _, status = plan.run_host(batch, logits=device_log_softmax)
-        t_align = time.perf_counter() - t0
-        t0 = time.perf_counter()
+            l_off = np.concatenate([[0], np.cumsum([len(x) for x in glabs])]).astype(np.int64)
+            labels = np.concatenate(glabs) if glabs else np.zeros(0, np.int32)
+            tm["read_normalise_and_labels_s"] = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            plan = None
+            try:
+                if align_fn is not None:
+                    path, lab, sc, _, status = align_fn(view, t_off, labels, l_off, V, beam_size, max_move, 0)
+                else:
+                    plan = AlignPlan(t_off, labels, l_off, V, beam_size, max_move, device=device)
+                    path, lab, sc, _, status = plan.run_host(view, logits=device_log_softmax)
+                tm["plan_and_align_s"] = time.perf_counter() - t0
+                t0 = time.perf_counter()
 
-        def save(n):
-            a, b = int(t_off[n]), int(t_off[n + 1])
-            np.savez(todo[mine[n]][2], best_path=path[a:b], best_labels=lab[a:b], best_scores=sc[a:b])
-        good = [n for n in range(len(mine)) if status[n] == ST_OK]
-        for n in range(len(mine)):
-            if status[n] != ST_OK:
-                first_bad = first_bad or int(status[n])
-            elif verbose:
-                print(f'Writing {todo[mine[n]][2]}')
-        with ThreadPoolExecutor(max(1, io_threads)) as ex:
-            list(ex.map(save, good))
-        written = [todo[mine[n]][2] for n in good]
-        t_write = time.perf_counter() - t0
+                def save(n):
+                    a, b = int(t_off[n]), int(t_off[n + 1])
+                    np.savez(todo[members[n]][2], best_path=path[a:b], best_labels=lab[a:b], best_scores=sc[a:b])
+                good = [n for n in range(len(members)) if status[n] == ST_OK]
+                for f in [io.submit(save, n) for n in good]:
+                    f.result()
+                tm["write_s"] = time.perf_counter() - t0
+            finally:
+                if plan is not None:   # (destroying a plan waits for the device: after the outputs are written)
+                    plan.close()
+            return [(members[n], int(status[n])) for n in range(len(members))], tm
+
+        try:
+            row0, jobs = 0, []
+            with ThreadPoolExecutor(len(groups)) as gex:
+                for members in groups:
+                    jobs.append(gex.submit(run_group, members, row0))
+                    row0 += int(sum(T_all[i] for i in members))
+                results = [j.result() for j in jobs]
+        finally:
+            io.shutdown()
+        status_of = {}
+        for res, tm in results:
+            status_of.update(res)
+            group_times.append(tm)
+        for i in mine:   # messages and return value in the order of the call
+            if status_of[i] != ST_OK:
+                first_bad = first_bad or status_of[i]
+            else:
+                if verbose:
+                    print(f'Writing {todo[i][2]}')
+                written.append(todo[i][2])
     if timings is not None:
-        timings.update(read_normalise_and_labels_s=t_read, plan_and_align_s=t_align, write_s=t_write,
-                       total_s=time.perf_counter() - t_start, frames=int(sum(T_all[i] for i in mine)),
-                       chapters=len(mine))
+        for key in ("read_normalise_and_labels_s", "plan_and_align_s", "write_s"):
+            timings[key] = max((tm.get(key, 0.0) for tm in group_times), default=0.0)
+        timings.update(total_s=time.perf_counter() - t_start, frames=int(sum(T_all[i] for i in mine)),
+                       chapters=len(mine), groups=[len(g) for g in groups] if mine else [])
     if world > 1:
         import torch.distributed as dist
         parts = [None] * world if rank == 0 else None

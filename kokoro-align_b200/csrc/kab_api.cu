@@ -947,6 +947,46 @@ int kab_ctc_best_path(const float *log_probs, int64_t T, int32_t V, const int32_
   return rc;
 }
 
+int kab_encode_transcript(const uint8_t *text, int64_t n_bytes, const int16_t *token_ids, int8_t *labels,
+                          int64_t *n_labels) {
+  if (n_bytes < 0 || !token_ids || !n_labels || (n_bytes > 0 && (!text || !labels))) return KAB_E_BAD_ARG;
+  int64_t n = 0, i = 0;
+  while (i < n_bytes) {
+    // one line [i, e): up to '\n'; a '\r' right before it is stripped (rstrip('\r\n'), transcript.py:64)
+    int64_t e = i;
+    while (e < n_bytes && text[e] != '\n') {
+      if (text[e] == '\r' && !(e + 1 < n_bytes && text[e + 1] == '\n')) return KAB_E_UNSUPPORTED;  // universal newlines
+      ++e;
+    }
+    int64_t le = e;
+    if (le > i && text[le - 1] == '\r') --le;
+    int64_t b = i;
+    while (b < le && text[b] != '|') ++b;
+    if (b >= le) return KAB_E_UNSUPPORTED;  // no second field: the reference raises IndexError (parts[1])
+    int64_t f = b + 1, fe = f;
+    while (fe < le && text[fe] != '|') ++fe;
+    // tokens of the voca field [f, fe): str.split() on runs of spaces (any other whitespace or a
+    // non-ASCII byte in the field leaves the plain case), ids by table, unknown tokens dropped
+    while (f < fe) {
+      while (f < fe && text[f] == ' ') ++f;
+      int64_t t = f;
+      while (t < fe && text[t] != ' ') {
+        if (text[t] < 32 || text[t] > 126) return KAB_E_UNSUPPORTED;
+        ++t;
+      }
+      const int64_t len = t - f;
+      if (len == 1 || len == 2) {
+        const int16_t id = token_ids[text[f] | (len == 2 ? (unsigned)text[f + 1] << 8 : 0u)];
+        if (id >= 0) labels[n++] = (int8_t)id;
+      }
+      f = t;
+    }
+    i = e + 1;
+  }
+  *n_labels = n;
+  return KAB_OK;
+}
+
 int kab_pool_trim(void) {
   DevPool &P = pool();
   std::lock_guard<std::mutex> lk(P.mu);

@@ -103,3 +103,50 @@ def test_npz_wire_format(tmp_path):
     assert align.npz_member_info(str(tmp_path / "stored.npz"), "indices")[0] == (2,)
     with pytest.raises(ValueError):
         align.npz_read_into(str(tmp_path / "stored.npz"), np.empty((5, 39), np.float32))
+
+
+def test_transcript_scanner_matches_text_path(tmp_path):
+    """kab_encode_transcript (byte scan in the C library) against the reference's control flow
+    (line.rstrip('\r\n').split('|')[1], ' '.join, str.split, vocabulary lookup) on fuzzed files:
+    same labels, same exception type; odd files fall back to the text path."""
+    from kokoro_align_b200 import align, encoder
+    rng = np.random.default_rng(0)
+    toks = list(encoder.VOCAB) + [',', '.', '!', '?', 'xx', 'abc', 'q', 'N:', 'a::', '~', '|']
+    n_plain = 0
+    for trial in range(300):
+        lines = []
+        for _ in range(rng.integers(0, 12)):
+            text = ''.join(rng.choice(list('あいう ab')) for _ in range(rng.integers(0, 5)))
+            voca = (' ' * rng.integers(1, 3)).join(rng.choice(toks[:-1]) for _ in range(rng.integers(0, 7)))
+            if rng.random() < 0.1:
+                voca = ' ' + voca + '  '
+            line = text + '|' + voca
+            r = rng.random()
+            if r < 0.10:
+                line += '|extra|more a i'
+            elif r < 0.13:
+                line = text                              # no '|': IndexError in both paths
+            elif r < 0.16:
+                line = text + '|' + voca.replace(' ', '\t', 1)
+            elif r < 0.18:
+                line = text + '|' + voca + '　a'
+            lines.append(line)
+        nlc = rng.choice(['\n', '\r\n']) if rng.random() < 0.9 else '\r'
+        content = (nlc.join(lines) + (nlc if rng.random() < 0.7 else '')).encode()
+        p = tmp_path / f"t{trial}.txt"
+        p.write_bytes(content)
+        res = []
+        for fn in (align._read_transcript_labels_text, align.read_transcript_labels):
+            try:
+                res.append(fn(str(p)))
+            except Exception as e:  # noqa: BLE001
+                res.append(type(e))
+        if isinstance(res[0], type):
+            assert res[1] is res[0]
+        else:
+            assert res[1].dtype == np.int8 and res[1].tolist() == res[0].tolist()
+        out, n = np.empty(len(content) // 2 + 1, np.int8), ctypes.c_int64(0)
+        from kokoro_align_b200 import _lib
+        n_plain += _lib.lib().kab_encode_transcript(content, len(content), align._ptr(align._TOKEN_IDS),
+                                                    align._ptr(out), ctypes.byref(n)) == 0
+    assert 60 < n_plain < 300

@@ -1,6 +1,8 @@
 """Parity of the CUDA path (through the C ABI) with the reference's golden vectors and with
 the CPU oracle on seeded inputs.  Bit-exact for best_path / best_labels / best_scores;
 final score within 1e-4 relative (north_star) -- asserted bit-equal in practice."""
+import os
+
 import numpy as np
 import pytest
 
@@ -289,7 +291,7 @@ def test_best_path_files_batch(kab, tmp_path, capsys):
     best_path(), existing outputs skipped with the reference's message."""
     rng = np.random.default_rng(77)
     logits_files, voca_files, out_files, ref_files = [], [], [], []
-    for n, (T, nl) in enumerate(((900, 9), (2600, 40), (130, 1))):
+    for n, (T, nl) in enumerate(((900, 9), (2600, 40), (130, 1), (5200, 70), (300, 3))):
         lf, vf = tmp_path / f"c{n}.logits.npz", tmp_path / f"c{n}.voca.txt"
         np.savez(lf, data=rng.standard_normal((T, 39)).astype(np.float32) * 3, indices=np.array([T], np.int32))
         with open(vf, "w") as f:
@@ -300,15 +302,26 @@ def test_best_path_files_batch(kab, tmp_path, capsys):
     for lf, vf, rf in zip(logits_files, voca_files, ref_files):
         kab.best_path(lf, vf, rf)
     np.savez(out_files[2], best_path=np.zeros(1, np.int32))  # already there: must be skipped
-    written = kab.best_path_files(logits_files, voca_files, out_files)
+    t = {}
+    written = kab.best_path_files(logits_files, voca_files, out_files, timings=t)
     out = capsys.readouterr().out
-    assert written == out_files[:2]
-    assert f"Skip writing {out_files[2]}" in out and f"Writing {out_files[0]}" in out
-    for of, rf in zip(out_files[:2], ref_files[:2]):
-        with np.load(of) as a, np.load(rf) as b:
+    want = [out_files[k] for k in (0, 1, 3, 4)]
+    assert written == want and t["groups"] == [2, 2]    # the two long chapters / the two short ones
+    assert f"Skip writing {out_files[2]}" in out
+    assert [ln for ln in out.splitlines() if ln.startswith("Writing")] == [f"Writing {w}" for w in want]
+    for k in (0, 1, 3, 4):
+        with np.load(out_files[k]) as a, np.load(ref_files[k]) as b:
             assert sorted(a.files) == ["best_labels", "best_path", "best_scores"]
             for key in a.files:
                 assert a[key].dtype == b[key].dtype and a[key].tobytes() == b[key].tobytes()
+    # one plan for everything gives the same files
+    for k in (0, 1, 3, 4):
+        os.unlink(out_files[k])
+    assert kab.best_path_files(logits_files, voca_files, out_files, verbose=False, pipeline=False) == want
+    for k in (0, 1, 3, 4):
+        with np.load(out_files[k]) as a, np.load(ref_files[k]) as b:
+            for key in a.files:
+                assert a[key].tobytes() == b[key].tobytes()
 
 
 @pytest.mark.parametrize("T,L", [(3000, 2500), (1003, 1500), (5, 300), (2047, 4000)])
