@@ -406,8 +406,9 @@ def best_path_files(logits_files, voca_files, best_path_files, skip_existing=Tru
             def load(n):
                 dst = view[int(t_off[n]):int(t_off[n + 1])]
                 npz_read_into(todo[members[n]][0], dst, info=infos[members[n]])
-                if not device_log_softmax:
-                    dst[...] = log_softmax(dst)
+                if not device_log_softmax:   # row blocks: numpy's temporaries stay in cache (same bits)
+                    for a in range(0, dst.shape[0], 2048):
+                        dst[a:a + 2048] = log_softmax(dst[a:a + 2048])
             # the logits stream into the batch buffer (readinto releases the GIL) while this
             # thread parses the transcripts
             loads = [io.submit(load, n) for n in range(len(members))]
