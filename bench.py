@@ -185,9 +185,14 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    # libraries (NCCL prints its version) write to fd 1: keep the real stdout for the one JSON line
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
-    from kokoro_align_b200 import align
+    from kokoro_align_b200 import align, parallel
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -199,6 +204,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
+    cpus = parallel.bind_host_to_gpu(local_rank) if world > 1 else None   # NUMA-local pinned buffers
     # ---- this rank's batch (weak scaling: every rank its own 10k segments / book)
     T, L, desc = workload_shapes(args.workload, args.seed + 7919 * rank, args.lattices)
     lp, t_off, labels, l_off = synth.make_batch_fast(T, L, seed=args.seed + 1 + 7919 * rank)
@@ -326,7 +332,8 @@ def main():
                        "kernel_classes": {"warp": int(info.n_class[0]), "band": int(info.n_class[1]),
                                           "generic": int(info.n_class[2])},
                        "l2": f"inputs ({n_frames * 39 * 4 / 1e6:.0f} MB log-probs + {int(info.backptr_bytes) / 1e6:.0f} MB backpointers per step) exceed the 126 MB L2",
-                       "parallelism": f"{world} independent ranks, no collective on the data path"},
+                       "parallelism": f"{world} independent ranks, no collective on the data path",
+                       "host_binding": (f"rank 0 bound to {len(cpus)} GPU-local cores (NVML affinity)" if cpus else "none")},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_frames * 39 * 4,
                     "d2h_bytes_per_step": n_frames * 12 + plan.B * 8, "ms_per_step": e2e_s / args.steps * 1e3},
             "e2e_raw_logits": {"value": cells_all * args.steps / e2e_logits_s, "unit": UNIT,
@@ -341,7 +348,7 @@ def main():
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kernel_ms},
             "cpu_baseline": cpu, "clocks": clocks,
         }
-        print(json.dumps(out), flush=True)
+        os.write(json_fd, (json.dumps(out) + "\n").encode())
     plan.close()
     if world > 1:
         dist.destroy_process_group()

@@ -111,3 +111,42 @@ def sum_over_ranks(x, group=None, device=None):
     t = torch.tensor([x], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return float(t.item())
+
+
+def bind_host_to_gpu(device):
+    """Pin this process to the CPU cores NVML reports as local to GPU `device` (same NUMA node /
+    PCIe root), BEFORE its pinned staging buffers are allocated: first-touch then places them in
+    the memory next to the GPU, so the H2D streams of the ranks of one box do not all cross the
+    same socket link.  Returns the cpu set, or None when NVML / affinity is unavailable."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            import torch
+            props_uuid = None
+            if torch.cuda.is_available():
+                props_uuid = str(torch.cuda.get_device_properties(device).uuid)
+            handle = None
+            if props_uuid:   # CUDA_VISIBLE_DEVICES may renumber the devices: match by UUID
+                for k in range(pynvml.nvmlDeviceGetCount()):
+                    h = pynvml.nvmlDeviceGetHandleByIndex(k)
+                    u = pynvml.nvmlDeviceGetUUID(h)
+                    u = u.decode() if isinstance(u, bytes) else u
+                    if props_uuid in u or u.replace("GPU-", "") == props_uuid:
+                        handle = h
+                        break
+            if handle is None:
+                handle = pynvml.nvmlDeviceGetHandleByIndex(device)
+            n_words = (os.cpu_count() + 63) // 64
+            words = pynvml.nvmlDeviceGetCpuAffinity(handle, n_words)
+        finally:
+            pynvml.nvmlShutdown()
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:  # noqa: BLE001  (no NVML, no permission, non-Linux: run unbound)
+        return None
