@@ -467,8 +467,8 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
 
   // parallel backtrack of the cluster band kernel: per-lattice block maps (KAB_BAND_SERIAL_BT=1
   // keeps the in-kernel single-thread walker: development / comparison)
-  // The maps kernel walks sum T * min(W, S) steps at ~1.2e12 steps/s (measured: the 36-chapter book,
-  // 2.7e9 steps, 2.2 ms); the in-kernel walkers run side by side, 40 ns per frame of the longest
+  // The maps kernel walks sum T * min(W, S) steps at ~1.85e12 steps/s (measured: the 36-chapter book,
+  // 2.7e9 steps, 1.46 ms); the in-kernel walkers run side by side, 40 ns per frame of the longest
   // lattice.  So the parallel traceback is used when the plan is a few lattices or very unequal
   // ones (a book), not for dozens of equal ones.  KAB_BAND_SERIAL_BT=0 forces it.
   bool par_bt = !pl->lists[Q_BAND].empty() && pl->band_nc > 0;
@@ -479,7 +479,7 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
       steps += (double)d.T * (double)std::min<int64_t>(W, 2 * (int64_t)d.L + 1);
       tmax = std::max(tmax, (double)d.T);
     }
-    par_bt = sb ? atoi(sb) == 0 : steps * 0.85e-12 <= 0.6 * tmax * 40e-9;
+    par_bt = sb ? atoi(sb) == 0 : steps * 0.55e-12 <= 0.6 * tmax * 40e-9;
   }
   if (par_bt) {
     for (const KabLattice &d : pl->lists[Q_BAND]) {

@@ -10,8 +10,8 @@
 //      EVERY state of the window at the block's last frame, one thread walks the block backwards
 //      and records where it leaves it: maps[block][v - lo] = state at the frame before the block.
 //      T x W steps in total (as many as the forward pass has cells), spread over the whole GPU.
-//      Walkers that start in inactive states produce values nobody looks up (moves are clamped so
-//      that they stay inside the workspace).
+//      Walkers that start in inactive states produce values nobody looks up (their addresses are
+//      derived from the ring position, which always stays inside the workspace).
 //   2. kab_bt_stitch_kernel (one CTA per lattice): thread 0 composes the maps from the forced end
 //      state down -- T / KAB_BT_BLOCK dependent table look-ups -- which yields the true entry
 //      state of every block; then the threads re-walk the blocks from their entry states, all
@@ -48,18 +48,28 @@ struct KabBtWalker {
     rs = slot - reg * KAB_BAND_OW;
     gp = bp + reg * stride + (size_t)g * 256;
   }
-  // one frame back (frame f of the current group); returns the state AT that frame (before the move)
+  // one frame back (frame f of the current group); returns the state AT that frame (before the move).
+  // The region change (once per ~370 frames of a walker) is a real branch into a non-inlined helper:
+  // predicated inline it was 9 of the 21 instructions of every step.
+  struct Wrap { int reg; long long delta; };
+  static __device__ __noinline__ Wrap wrap_region(int reg, int NWT, long long stride) {
+    Wrap w;
+    const bool first = reg == 0;
+    w.reg = first ? NWT - 1 : reg - 1;
+    w.delta = first ? (long long)(NWT - 1) * stride : -stride;
+    return w;
+  }
   __device__ __forceinline__ int step(int f, int NWT, int64_t stride) {
     const unsigned int byte = gp[((rs >> 2) << 3) + f];
     const int at = v;
-    const int mv = min((int)((byte >> (2 * (rs & 3))) & 3u), v);  // (clamp: only garbage walkers hit it)
-    v -= mv;
-    rs -= mv;
+    const int mv = (int)((byte >> (2 * (rs & 3))) & 3u);
+    v -= mv;  // (a walker that started in an inactive state may run below 0: its value is never used,
+    rs -= mv;  //  and the addresses come from rs / reg, which stay inside the workspace)
     if (rs < 0) {  // into the region below (a move crosses at most one boundary)
       rs += KAB_BAND_OW;
-      const bool wrap = reg == 0;
-      reg = wrap ? NWT - 1 : reg - 1;
-      gp += wrap ? (int64_t)(NWT - 1) * stride : -stride;
+      const Wrap w = wrap_region(reg, NWT, stride);
+      reg = w.reg;
+      gp += w.delta;
     }
     return at;
   }
