@@ -17,7 +17,7 @@
 //     fence, no flag and no mbarrier on the recurrence; the consumer's ghost lanes load message
 //     g at the start of group g and check it at the start of group g+1 (kab_wide.cuh uses the
 //     same scheme).  The first version used st.async + mbarriers over DSMEM: every mbarrier
-//     round trip costs a lone warp 100-250 cycles and the ring ran in lockstep (DESIGN.md 3.4).
+//     round trip costs a lone warp 100-250 cycles and the ring ran in lockstep (DESIGN.md 3.3).
 //     A warp whose 24 ghost states are outside the window does not look at its messages at all,
 //     so the ring is a chain whose head runs free, and a warp that (re)joins the chain first
 //     waits until its neighbour is two groups ahead: the wavefront that hides the L2 latency;
