@@ -145,6 +145,15 @@ int kab_encode_transcript(const uint8_t *text, int64_t n_bytes, const int16_t *t
                           int8_t *labels, int64_t *n_labels);
 
 /*
+ * encoder.py:28, the regular expression of merge_repeated -- re.sub(r'(.+)( \1)+', r'\1', text)
+ * -- which align() (align.py:159) runs on the decoded labels of every segment and which costs the
+ * backtracking engine ~30 ms per segment (90 s per book).  Same leftmost / greedy semantics, byte
+ * for byte, for ASCII text without newlines; KAB_E_UNSUPPORTED otherwise (the Python mirror then
+ * uses `re`).  `out` needs room for n bytes.  Host-only.
+ */
+int kab_merge_repeated(const uint8_t *text, int64_t n_bytes, uint8_t *out, int64_t *n_out);
+
+/*
  * Device memory of destroyed plans is kept in a per-device pool and reused by later plans (the
  * drop-in ctc_best_path() builds one plan per call; cudaFree synchronises the device).  This
  * returns every cached block to the driver.

@@ -22,7 +22,7 @@ ST_OK, ST_DEAD_BAND, ST_BAD_LABEL, ST_NONFINITE = 0, 1, 2, 3
 
 EXPORTS = ["kab_version", "kab_error_string", "kab_last_cuda_error", "kab_device_count",
            "kab_plan_create", "kab_plan_get_info", "kab_plan_destroy", "kab_plan_run_device",
-           "kab_plan_run_host", "kab_plan_run_host_logits", "kab_log_softmax_device", "kab_ctc_best_path", "kab_encode_transcript", "kab_pool_trim", "kab_host_alloc", "kab_host_free"]
+           "kab_plan_run_host", "kab_plan_run_host_logits", "kab_log_softmax_device", "kab_ctc_best_path", "kab_encode_transcript", "kab_merge_repeated", "kab_pool_trim", "kab_host_alloc", "kab_host_free"]
 
 
 class PlanInfo(ctypes.Structure):
@@ -87,6 +87,7 @@ def lib():
     L.kab_log_softmax_device.argtypes = [vp, vp, i64, i32, vp]
     L.kab_ctc_best_path.argtypes = [vp, i64, i32, vp, i64, i32, i32, vp, vp, vp, vp, vp]
     L.kab_encode_transcript.argtypes = [vp, i64, vp, vp, ctypes.POINTER(i64)]
+    L.kab_merge_repeated.argtypes = [vp, i64, vp, ctypes.POINTER(i64)]
     L.kab_host_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_size_t]
     L.kab_host_free.argtypes = [vp]
     for name in EXPORTS:

@@ -987,6 +987,32 @@ int kab_encode_transcript(const uint8_t *text, int64_t n_bytes, const int16_t *t
   return KAB_OK;
 }
 
+int kab_merge_repeated(const uint8_t *text, int64_t n, uint8_t *out, int64_t *n_out) {
+  // re.sub(r'(.+)( \1)+', r'\1', text), encoder.py:28, for text without '\n' (where '.' is any
+  // character): leftmost match, group 1 greedy (longest first), then as many " \1" as fit; a match
+  // is replaced by group 1 and the scan continues behind it.
+  if (n < 0 || !n_out || (n > 0 && (!text || !out))) return KAB_E_BAD_ARG;
+  for (int64_t k = 0; k < n; ++k)
+    if (text[k] == '\n' || text[k] >= 0x80) return KAB_E_UNSUPPORTED;  // '.' stops at newlines; bytes != characters
+  int64_t i = 0, o = 0;
+  while (i < n) {
+    int64_t m = (n - i - 1) / 2;  // group 1 = text[i, i+m), followed by ' ' and the same m bytes
+    for (; m >= 1; --m)
+      if (text[i + m] == ' ' && memcmp(text + i, text + i + m + 1, (size_t)m) == 0) break;
+    if (m < 1) {
+      out[o++] = text[i++];
+      continue;
+    }
+    int64_t e = i + 2 * m + 1;
+    while (e + m + 1 <= n && text[e] == ' ' && memcmp(text + i, text + e + 1, (size_t)m) == 0) e += m + 1;
+    memcpy(out + o, text + i, (size_t)m);
+    o += m;
+    i = e;
+  }
+  *n_out = o;
+  return KAB_OK;
+}
+
 int kab_pool_trim(void) {
   DevPool &P = pool();
   std::lock_guard<std::mutex> lk(P.mu);

@@ -150,3 +150,28 @@ def test_transcript_scanner_matches_text_path(tmp_path):
         n_plain += _lib.lib().kab_encode_transcript(content, len(content), align._ptr(align._TOKEN_IDS),
                                                     align._ptr(out), ctypes.byref(n)) == 0
     assert 60 < n_plain < 300
+
+
+def test_merge_repeated_matches_the_regular_expression():
+    """encoder.merge_repeated evaluates encoder.py:28's regex in C (kab_merge_repeated): identical
+    to `re` on random token runs, double spaces, sub-token matches ('k ky'), and it falls back to
+    `re` for text the byte scan does not take."""
+    import re
+    from kokoro_align_b200 import encoder
+
+    def ref(text):
+        r = re.sub(r'(.+)( \1)+', r'\1', text).replace(' _', '').replace('_ ', '')
+        return '' if r == '_' else r
+    rng = np.random.default_rng(5)
+    V = list(encoder.VOCAB)
+    cases = ['', '_', '_ _', 'k ky', 'a a:', 'a a a', 'a a a a', 'a b a b', 'a b a b a b c', 'x  x', 'ab ab\nab ab', 'あ あ']
+    for _ in range(1500):
+        toks = []
+        for _ in range(int(rng.integers(0, 40))):
+            toks += [V[int(rng.integers(0, rng.choice([3, 6, 39])))]] * int(rng.integers(1, 6))
+        text = ' '.join(toks)
+        if rng.random() < 0.1:
+            text = text.replace(' ', '  ', 1)
+        cases.append(text)
+    for text in cases:
+        assert encoder.merge_repeated(text) == ref(text), repr(text)
