@@ -994,11 +994,21 @@ int kab_merge_repeated(const uint8_t *text, int64_t n, uint8_t *out, int64_t *n_
   if (n < 0 || !n_out || (n > 0 && (!text || !out))) return KAB_E_BAD_ARG;
   for (int64_t k = 0; k < n; ++k)
     if (text[k] == '\n' || text[k] >= 0x80) return KAB_E_UNSUPPORTED;  // '.' stops at newlines; bytes != characters
+  std::vector<int64_t> spaces;  // positions of ' ', ascending: the only places group 1 can end
+  for (int64_t k = 0; k < n; ++k)
+    if (text[k] == ' ') spaces.push_back(k);
   int64_t i = 0, o = 0;
+  size_t s_lo = 0;  // first space position > i
   while (i < n) {
-    int64_t m = (n - i - 1) / 2;  // group 1 = text[i, i+m), followed by ' ' and the same m bytes
-    for (; m >= 1; --m)
-      if (text[i + m] == ' ' && memcmp(text + i, text + i + m + 1, (size_t)m) == 0) break;
+    while (s_lo < spaces.size() && spaces[s_lo] <= i) ++s_lo;
+    // group 1 = text[i, i+m), followed by ' ' at i+m and the same m bytes: longest m first
+    const int64_t m_max = (n - i - 1) / 2;
+    size_t k = std::upper_bound(spaces.begin() + (std::ptrdiff_t)s_lo, spaces.end(), i + m_max) - spaces.begin();
+    int64_t m = 0;
+    while (k > s_lo) {
+      const int64_t cand = spaces[--k] - i;
+      if (text[i] == text[i + cand + 1] && memcmp(text + i, text + i + cand + 1, (size_t)cand) == 0) { m = cand; break; }
+    }
     if (m < 1) {
       out[o++] = text[i++];
       continue;

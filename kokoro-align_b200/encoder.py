@@ -17,7 +17,7 @@ def encode_text(text):
 
 
 def decode_text(encoded):
-    return ' '.join(VOCAB[n] for n in encoded)
+    return ' '.join(map(VOCAB.__getitem__, np.asarray(encoded).tolist()))
 
 
 def merge_repeated(text):
