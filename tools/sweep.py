@@ -1,5 +1,5 @@
 """BASELINE config 5: synthetic sweep T x L (x beam) -> cells/s and algorithmic GB/s per point.
-    python tools/sweep.py [--quick] > profiles/rNN_sweep.json
+    python tools/sweep.py [--quick] [--wide-v | --unbanded] > profiles/rNN_sweep.json
 Each point is a batch of identical-shape lattices sized to fill the GPU (B lattices), timed
 device-resident with CUDA events (best of 3).  Points with S > 2T are skipped."""
 import json
@@ -24,6 +24,10 @@ points = [(T, L, 39) for T in Ts for L in Ls]
 # (V = 4096: compact per-lattice copy of the used columns, kab_compact.cuh)
 wide_v = [(1000, 100, 256), (10000, 1000, 256), (1000, 100, 512), (1000, 100, 4096), (10000, 1000, 4096)]
 points = wide_v if "--wide-v" in sys.argv else points + ([] if quick else wide_v)
+unbanded = "--unbanded" in sys.argv   # beam_size covers the lattice (config 5: where T*S <= 1e11)
+if unbanded:
+    # (S <= 1000: the default band already covers the lattice, same numbers as the banded sweep)
+    points = [(T, L, 39) for T in Ts for L in Ls if 2 * L + 1 > 1000 and T * (2 * L + 1) <= 1.001e11]
 for T, L, V in points:
     if True:
         S = 2 * L + 1
@@ -31,8 +35,11 @@ for T, L, V in points:
             continue
         frames_budget = 6_000_000 * 39 // V          # keep inputs below ~1 GB per point
         B = int(max(1, min(4096, frames_budget // T)))
+        if unbanded and S > 248:                      # band / wide kernels: cells, not frames, bound the point
+            B = int(max(1, min(B, 4 * 10 ** 10 // (T * S))))
         lp, t_off, labels, l_off = synth.make_batch_fast(np.full(B, T), np.full(B, L), V=V, seed=5000 + T % 97 + L % 89)
-        plan = align.AlignPlan(t_off, labels, l_off, V)
+        beam = 2 * S + 2 if unbanded else 1000
+        plan = align.AlignPlan(t_off, labels, l_off, V, beam_size=beam)
         d_lp = torch.from_numpy(lp).cuda()
         for _ in range(2):
             o = plan.run_torch(d_lp)
@@ -44,7 +51,7 @@ for T, L, V in points:
             best = min(best, e0.elapsed_time(e1))
         st = o[4].cpu().numpy()
         info = plan.info
-        rec = dict(T=T, L=L, S=S, B=B, V=V, beam_size=1000, ms=best, status_ok=bool((st == 0).all()),
+        rec = dict(T=T, L=L, S=S, B=B, V=V, beam_size=beam, ms=best, status_ok=bool((st == 0).all()),
                    cells_eval=int(info.cells_eval), cells_nominal=int(info.cells_nominal),
                    cells_eval_per_s=info.cells_eval / best * 1e3, cells_nominal_per_s=info.cells_nominal / best * 1e3,
                    algorithmic_gbs=info.algorithmic_bytes / best / 1e6, hbm_frac=info.algorithmic_bytes / best / 1e6 / peak,
