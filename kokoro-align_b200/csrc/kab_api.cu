@@ -25,6 +25,7 @@
 #include "kab_generic.cuh"
 #include "kab_softmax.cuh"
 #include "kab_warp.cuh"
+#include "kab_pool.h"  // pool_malloc / pool_free / pool_trim_device
 
 namespace {
 
@@ -40,83 +41,6 @@ int cuda_fail(cudaError_t e, const char *what) {
     if (e_ != cudaSuccess) return cuda_fail(e_, #call);   \
   } while (0)
 
-// ---- device memory pool.  The drop-in call ctc_best_path() builds and destroys a plan per
-// lattice, as the reference's per-chapter loop does (run_example.py:247-254): a dozen cudaMalloc /
-// cudaFree pairs per call, and every cudaFree synchronises the device.  Freed blocks are kept per
-// device (size classes of <= 12.5 % slack) and handed out again; kab_pool_trim() returns them to
-// the driver, and the pool trims itself beyond POOL_CAP_BYTES per device.
-constexpr int POOL_MAX_DEV = 64;
-constexpr size_t POOL_CAP_BYTES = (size_t)16 << 30;
-struct DevPool {
-  std::mutex mu;
-  std::multimap<size_t, void *> free_blocks[POOL_MAX_DEV];
-  std::unordered_map<void *, std::pair<size_t, int>> live;  // block -> (class size, device)
-  size_t cached[POOL_MAX_DEV] = {};
-};
-DevPool &pool() {
-  static DevPool *p = new DevPool();  // never destroyed: plans may be freed during interpreter exit
-  return *p;
-}
-size_t pool_class(size_t bytes) {
-  if (bytes < 256) return 256;
-  int lg = 63 - __builtin_clzll((unsigned long long)bytes);
-  const size_t step = std::max<size_t>(256, (size_t)1 << (lg > 3 ? lg - 3 : 0));
-  return (bytes + step - 1) / step * step;
-}
-void pool_trim_device(DevPool &P, int dev, size_t keep_bytes) {  // P.mu held
-  int cur = 0;
-  cudaGetDevice(&cur);
-  bool switched = false;
-  while (P.cached[dev] > keep_bytes && !P.free_blocks[dev].empty()) {
-    auto it = std::prev(P.free_blocks[dev].end());  // largest first
-    if (!switched && cur != dev) { cudaSetDevice(dev); switched = true; }
-    cudaFree(it->second);
-    P.cached[dev] -= it->first;
-    P.free_blocks[dev].erase(it);
-  }
-  if (switched) cudaSetDevice(cur);
-}
-cudaError_t pool_malloc(void **out, size_t bytes) {  // on the current device
-  *out = nullptr;
-  int dev = 0;
-  cudaError_t e = cudaGetDevice(&dev);
-  if (e != cudaSuccess) return e;
-  const size_t cls = pool_class(bytes);
-  DevPool &P = pool();
-  std::lock_guard<std::mutex> lk(P.mu);
-  if (dev < POOL_MAX_DEV) {
-    auto it = P.free_blocks[dev].lower_bound(cls);
-    if (it != P.free_blocks[dev].end() && it->first == cls) {
-      *out = it->second;
-      P.cached[dev] -= cls;
-      P.free_blocks[dev].erase(it);
-      P.live[*out] = {cls, dev};
-      return cudaSuccess;
-    }
-  }
-  e = cudaMalloc(out, cls);
-  if (e != cudaSuccess && dev < POOL_MAX_DEV && P.cached[dev]) {  // out of memory: give the cache back, retry
-    cudaGetLastError();
-    pool_trim_device(P, dev, 0);
-    e = cudaMalloc(out, cls);
-  }
-  if (e == cudaSuccess) P.live[*out] = {cls, dev};
-  return e;
-}
-void pool_free(void *ptr) {
-  if (!ptr) return;
-  DevPool &P = pool();
-  std::lock_guard<std::mutex> lk(P.mu);
-  auto it = P.live.find(ptr);
-  if (it == P.live.end()) { cudaFree(ptr); return; }
-  const size_t cls = it->second.first;
-  const int dev = it->second.second;
-  P.live.erase(it);
-  if (dev >= POOL_MAX_DEV) { cudaFree(ptr); return; }
-  P.free_blocks[dev].emplace(cls, ptr);
-  P.cached[dev] += cls;
-  if (P.cached[dev] > POOL_CAP_BYTES) pool_trim_device(P, dev, POOL_CAP_BYTES / 2);
-}
 int sm_count_of(int device, int *out) {  // (cudaGetDeviceProperties takes milliseconds; this is cached)
   static int cache[POOL_MAX_DEV] = {};
   if (device >= 0 && device < POOL_MAX_DEV && cache[device]) { *out = cache[device]; return KAB_OK; }
@@ -947,82 +871,6 @@ int kab_ctc_best_path(const float *log_probs, int64_t T, int32_t V, const int32_
   return rc;
 }
 
-int kab_encode_transcript(const uint8_t *text, int64_t n_bytes, const int16_t *token_ids, int8_t *labels,
-                          int64_t *n_labels) {
-  if (n_bytes < 0 || !token_ids || !n_labels || (n_bytes > 0 && (!text || !labels))) return KAB_E_BAD_ARG;
-  int64_t n = 0, i = 0;
-  while (i < n_bytes) {
-    // one line [i, e): up to '\n'; a '\r' right before it is stripped (rstrip('\r\n'), transcript.py:64)
-    int64_t e = i;
-    while (e < n_bytes && text[e] != '\n') {
-      if (text[e] == '\r' && !(e + 1 < n_bytes && text[e + 1] == '\n')) return KAB_E_UNSUPPORTED;  // universal newlines
-      ++e;
-    }
-    int64_t le = e;
-    if (le > i && text[le - 1] == '\r') --le;
-    int64_t b = i;
-    while (b < le && text[b] != '|') ++b;
-    if (b >= le) return KAB_E_UNSUPPORTED;  // no second field: the reference raises IndexError (parts[1])
-    int64_t f = b + 1, fe = f;
-    while (fe < le && text[fe] != '|') ++fe;
-    // tokens of the voca field [f, fe): str.split() on runs of spaces (any other whitespace or a
-    // non-ASCII byte in the field leaves the plain case), ids by table, unknown tokens dropped
-    while (f < fe) {
-      while (f < fe && text[f] == ' ') ++f;
-      int64_t t = f;
-      while (t < fe && text[t] != ' ') {
-        if (text[t] < 32 || text[t] > 126) return KAB_E_UNSUPPORTED;
-        ++t;
-      }
-      const int64_t len = t - f;
-      if (len == 1 || len == 2) {
-        const int16_t id = token_ids[text[f] | (len == 2 ? (unsigned)text[f + 1] << 8 : 0u)];
-        if (id >= 0) labels[n++] = (int8_t)id;
-      }
-      f = t;
-    }
-    i = e + 1;
-  }
-  *n_labels = n;
-  return KAB_OK;
-}
-
-int kab_merge_repeated(const uint8_t *text, int64_t n, uint8_t *out, int64_t *n_out) {
-  // re.sub(r'(.+)( \1)+', r'\1', text), encoder.py:28, for text without '\n' (where '.' is any
-  // character): leftmost match, group 1 greedy (longest first), then as many " \1" as fit; a match
-  // is replaced by group 1 and the scan continues behind it.
-  if (n < 0 || !n_out || (n > 0 && (!text || !out))) return KAB_E_BAD_ARG;
-  for (int64_t k = 0; k < n; ++k)
-    if (text[k] == '\n' || text[k] >= 0x80) return KAB_E_UNSUPPORTED;  // '.' stops at newlines; bytes != characters
-  std::vector<int64_t> spaces;  // positions of ' ', ascending: the only places group 1 can end
-  for (int64_t k = 0; k < n; ++k)
-    if (text[k] == ' ') spaces.push_back(k);
-  int64_t i = 0, o = 0;
-  size_t s_lo = 0;  // first space position > i
-  while (i < n) {
-    while (s_lo < spaces.size() && spaces[s_lo] <= i) ++s_lo;
-    // group 1 = text[i, i+m), followed by ' ' at i+m and the same m bytes: longest m first
-    const int64_t m_max = (n - i - 1) / 2;
-    size_t k = std::upper_bound(spaces.begin() + (std::ptrdiff_t)s_lo, spaces.end(), i + m_max) - spaces.begin();
-    int64_t m = 0;
-    while (k > s_lo) {
-      const int64_t cand = spaces[--k] - i;
-      if (text[i] == text[i + cand + 1] && memcmp(text + i, text + i + cand + 1, (size_t)cand) == 0) { m = cand; break; }
-    }
-    if (m < 1) {
-      out[o++] = text[i++];
-      continue;
-    }
-    int64_t e = i + 2 * m + 1;
-    while (e + m + 1 <= n && text[e] == ' ' && memcmp(text + i, text + e + 1, (size_t)m) == 0) e += m + 1;
-    memcpy(out + o, text + i, (size_t)m);
-    o += m;
-    i = e;
-  }
-  *n_out = o;
-  return KAB_OK;
-}
-
 int kab_pool_trim(void) {
   DevPool &P = pool();
   std::lock_guard<std::mutex> lk(P.mu);
@@ -1042,3 +890,5 @@ int kab_host_free(void *ptr) {
 }
 
 }  // extern "C"
+
+#include "kab_text.h"  // kab_encode_transcript, kab_merge_repeated (host-only text helpers)
