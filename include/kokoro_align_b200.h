@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define KAB_VERSION 100 /* 0.1.0 */
+#define KAB_VERSION 200 /* 0.2.0 */
 
 /* return codes */
 #define KAB_OK 0
@@ -113,6 +113,20 @@ int kab_log_softmax_device(const float *d_logits, float *d_log_probs, int64_t n_
                            int32_t vocab_size, void *stream);
 
 /*
+ * The hand-off from the acoustic model.  predict() (train.py:215-229)
+ * receives a padded, time-major batch logits [t_max, n_seq, V] with lens [n_seq] from the encoder
+ * and appends logits[:len_j, j, :] of every sequence j to the chapter's *.logits.npz.  This does
+ * the same append plus align.py:116-117 on the device: row d_out_off[j] + t of d_log_probs =
+ * log_softmax(logits[t, j, :]), d_out_off int64 [n_seq + 1] on the device (packed row offsets of
+ * this batch inside the chapter buffer; d_out_off[0] is the first row written, n_rows =
+ * d_out_off[n_seq] - d_out_off[0] -- pass d_log_probs already offset so that d_out_off[0] == 0).
+ * vocab_size <= 128.  Asynchronous on `stream`.
+ */
+int kab_log_softmax_pack_device(const float *d_logits_tbv, int64_t t_max, int64_t n_seq,
+                                int32_t vocab_size, const int64_t *d_out_off, float *d_log_probs,
+                                int64_t n_rows, void *stream);
+
+/*
  * kab_plan_run_host for RAW LOGITS (the `*.logits.npz` rows of align.py:113-114): copies them to
  * the device, normalises them there (kab_log_softmax_device, in place) and aligns.  Opt-in: the
  * alignment is exact for the device's log-probs, which differ from numpy's by a few ulp.
@@ -121,6 +135,49 @@ int kab_log_softmax_device(const float *d_logits, float *d_log_probs, int64_t n_
 int kab_plan_run_host_logits(kab_plan *plan, const float *h_logits, int32_t *h_best_path,
                              int32_t *h_best_labels, float *h_best_scores, float *h_final_score,
                              int32_t *h_status, float *h_log_probs);
+
+/*
+ * Per-segment statistics of an alignment -- everything the reference's align() (align.py:127-169)
+ * reads from the three T-length arrays -- computed on the device:
+ *   text_start       best_path[audio_start] // 2                          align.py:131,151
+ *   text_end         best_path[audio_end] // 2, or -1 when audio_end >= T ("len(aligner)", align.py:152)
+ *   non_blanks       np.sum(best_labels[a:b] != 0)                        align.py:160
+ *   non_blanks_score np.sum(best_scores[a:b][best_labels[a:b] != 0])      align.py:161
+ *   all_score        np.sum(best_scores[a:b])                             align.py:162
+ * both sums in numpy's float32 pairwise order, bit for bit.  status = the lattice's KAB_ST_*, or -1
+ * when audio_start lies outside the lattice (the reference raises IndexError there).
+ */
+typedef struct kab_segment_record {
+  int32_t text_start, text_end, non_blanks;
+  float non_blanks_score, all_score;
+  int32_t status;
+} kab_segment_record;
+
+/*
+ * Segments are given the way the reference stores them (`indices` of *.mfcc.npz, preprocess.py:12-35:
+ * cumulative segment ENDS in frames, relative to their lattice), concatenated over the batch:
+ * seg_lat_off int64 [B+1] (segments of lattice b = seg_lat_off[b] .. seg_lat_off[b+1]-1), seg_end
+ * int64 [n_segments] (non-decreasing inside a lattice).  Device pointers; the arrays are the outputs
+ * of kab_plan_run_device on the same plan; d_labels_u8 (may be NULL) receives best_labels as bytes
+ * [sum T] (the `decoded` column of align() needs the per-frame labels; vocab_size <= 256).
+ * Asynchronous on `stream`.
+ */
+int kab_plan_segment_stats_device(kab_plan *plan, const int32_t *d_best_path, const int32_t *d_best_labels,
+                                  const float *d_best_scores, const int32_t *d_status, int64_t n_segments,
+                                  const int64_t *d_seg_lat_off, const int64_t *d_seg_end,
+                                  kab_segment_record *d_records, uint8_t *d_labels_u8, void *stream);
+
+/*
+ * kab_plan_run_host (is_logits = 0) / kab_plan_run_host_logits (is_logits != 0) that also -- or
+ * only -- returns the segment records: h_best_path / h_best_labels / h_best_scores may be NULL
+ * (all three), and then 24 bytes per segment come back instead of 12 bytes per frame;
+ * h_labels_u8 (may be NULL) as above.  KAB_E_BAD_ARG for segment ends that decrease.
+ */
+int kab_plan_run_host_segments(kab_plan *plan, const float *h_log_probs_or_logits, int32_t is_logits,
+                               int64_t n_segments, const int64_t *h_seg_lat_off, const int64_t *h_seg_end,
+                               kab_segment_record *h_records, uint8_t *h_labels_u8, int32_t *h_best_path,
+                               int32_t *h_best_labels, float *h_best_scores, float *h_final_score,
+                               int32_t *h_status);
 
 /*
  * One-shot single lattice with host buffers == kokoro_align/align.py:43

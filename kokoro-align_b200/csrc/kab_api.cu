@@ -6,6 +6,7 @@
 #include "../../include/kokoro_align_b200.h"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <map>
 #include <mutex>
@@ -24,6 +25,7 @@
 #include "kab_compact.cuh"
 #include "kab_generic.cuh"
 #include "kab_softmax.cuh"
+#include "kab_segstats.cuh"
 #include "kab_warp.cuh"
 #include "kab_pool.h"  // pool_malloc / pool_free / pool_trim_device
 
@@ -42,14 +44,48 @@ int cuda_fail(cudaError_t e, const char *what) {
   } while (0)
 
 int sm_count_of(int device, int *out) {  // (cudaGetDeviceProperties takes milliseconds; this is cached)
-  static int cache[POOL_MAX_DEV] = {};
-  if (device >= 0 && device < POOL_MAX_DEV && cache[device]) { *out = cache[device]; return KAB_OK; }
+  static std::atomic<int> cache[POOL_MAX_DEV];
+  if (device >= 0 && device < POOL_MAX_DEV) {
+    const int c = cache[device].load(std::memory_order_relaxed);
+    if (c) { *out = c; return KAB_OK; }
+  }
   int n = 0;
   KAB_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device));
-  if (device >= 0 && device < POOL_MAX_DEV) cache[device] = n;
+  if (device >= 0 && device < POOL_MAX_DEV) cache[device].store(n, std::memory_order_relaxed);
   *out = n;
   return KAB_OK;
 }
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per-function, per-device GLOBAL state, while the
+// size a launch needs depends on the plan (vocabulary, beam).  Several plans may be alive at once
+// (best_path_files runs two side by side), so the attribute only ever GROWS: the largest size any
+// plan of this process has asked for, kept under a mutex.  A launch may use any size up to it.
+cudaError_t ensure_dyn_smem(const void *fn, int device, size_t bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<const void *, int>, size_t> have;
+  std::lock_guard<std::mutex> lk(mu);
+  size_t &cur = have[{fn, device}];
+  if (bytes <= cur) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) cur = bytes;
+  return e;
+}
+
+// The ABI entry points run on the plan's device and give the caller's current device back.
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  cudaError_t enter(int device) {
+    cudaError_t e = cudaGetDevice(&prev);
+    if (e != cudaSuccess) return e;
+    if (prev != device) {
+      e = cudaSetDevice(device);
+      switched = e == cudaSuccess;
+    }
+    return e;
+  }
+  ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
 // KAB_TRACE=1: wall time of the host-side phases of every call, to stderr (development)
 struct Trace {
   bool on;
@@ -95,6 +131,7 @@ struct kab_plan {
   int32_t Vc = 0;              // > 0: the staged kernels work on compact log-probs of Vc columns (kab_compact.cuh)
   int32_t *d_gather = nullptr;  // [B][Vc] compact column -> column of log_probs (= label value)
   float *d_lpc = nullptr;       // [sum T][Vc] compact log-probs
+  int32_t *d_nonfinite = nullptr;  // [B] compact path: a non-finite value anywhere in the lattice's rows
   int max_T[4] = {0, 0, 0, 0};  // longest lattice of every work list (grid of the compaction kernels)
   int sm_count = 0;
   int32_t stage_frames = 0, stage_bytes = 0;
@@ -134,33 +171,83 @@ struct kab_plan {
   cudaStream_t s_in = nullptr, s_out = nullptr;
   std::vector<cudaEvent_t> ev_in, ev_cmp;
   bool is_child = false;
-  // buffers of kab_plan_run_host
+  // streams kab_plan_run_device was last called on, each with an event recorded behind the plan's
+  // kernels: kab_plan_destroy waits for THESE, not for the whole device
+  std::vector<std::pair<cudaStream_t, cudaEvent_t>> run_events;
+  // buffers of kab_plan_run_host (host_ready: streams, buffers and segment plans all exist)
+  bool host_ready = false;
   cudaStream_t stream = nullptr;
   float *d_lp = nullptr;
   int32_t *d_path = nullptr, *d_lab = nullptr, *d_st = nullptr;
   float *d_sc = nullptr, *d_fs = nullptr;
+  // segment statistics (kab_segstats.cuh)
+  int64_t *d_t_off = nullptr;      // [B+1] first row of every lattice
+  float *d_seg_scratch = nullptr;  // [sum T] compacted voiced scores
+  int64_t *d_seg_off = nullptr;    // kab_plan_run_host_segments: [B+1] + [n_segments] boundaries on the device
+  KabSegmentRecord *d_seg_rec = nullptr;
+  uint8_t *d_lab8 = nullptr;
+  int64_t seg_cap = 0;
 };
 
 namespace {
 
-int plan_free(kab_plan *pl) {
-  if (!pl) return KAB_OK;
-  Trace tr("kab_plan_destroy");
-  cudaSetDevice(pl->device);
-  // pooled blocks may be handed to another plan at once, so nothing of this one may still be in
-  // flight on any stream (kab_plan_run_device is asynchronous); cudaFree used to imply the same wait
-  if (!pl->is_child) cudaDeviceSynchronize();
-  for (int q = 0; q < N_QUEUES; ++q) pool_free(pl->d_lists[q]);
-  pool_free(pl->d_col16); pool_free(pl->d_raw); pool_free(pl->d_bp); pool_free(pl->d_scratch);
-  pool_free(pl->d_queue); pool_free(pl->d_status_init); pool_free(pl->d_wide_ws); pool_free(pl->d_band_fifo); pool_free(pl->d_bt_meta); pool_free(pl->d_bt_maps); pool_free(pl->d_bt_entry); pool_free(pl->d_end_state); pool_free(pl->d_gather); pool_free(pl->d_lpc);
+int plan_free(kab_plan *pl);
+
+// kab_plan_destroy waits for the plan's launches (an event behind the last one on every stream it
+// was run on), not for the whole device
+int record_run_event(kab_plan *pl, cudaStream_t stream) {
+  if (pl->is_child) return KAB_OK;  // (the parent's streams are synchronised by the parent)
+  cudaEvent_t ev = nullptr;
+  for (auto &se : pl->run_events)
+    if (se.first == stream) ev = se.second;
+  if (!ev) {
+    KAB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    pl->run_events.emplace_back(stream, ev);
+  }
+  KAB_CUDA(cudaEventRecord(ev, stream));
+  return KAB_OK;
+}
+
+// Streams, buffers and child plans of kab_plan_run_host (also the undo of a failed set-up).
+void host_teardown(kab_plan *pl) {
+  for (kab_plan *c : pl->segs) plan_free(c);
+  pl->segs.clear();
+  pl->seg_b0.clear();
+  for (cudaEvent_t e : pl->ev_in) cudaEventDestroy(e);
+  for (cudaEvent_t e : pl->ev_cmp) cudaEventDestroy(e);
+  pl->ev_in.clear();
+  pl->ev_cmp.clear();
   pool_free(pl->d_lp); pool_free(pl->d_path); pool_free(pl->d_lab); pool_free(pl->d_st);
-  pool_free(pl->d_sc); pool_free(pl->d_fs);
+  pool_free(pl->d_sc); pool_free(pl->d_fs); pool_free(pl->d_seg_off); pool_free(pl->d_seg_rec); pool_free(pl->d_lab8);
+  pl->d_lp = nullptr; pl->d_path = nullptr; pl->d_lab = nullptr; pl->d_st = nullptr;
+  pl->d_sc = nullptr; pl->d_fs = nullptr; pl->d_seg_off = nullptr; pl->d_seg_rec = nullptr; pl->d_lab8 = nullptr;
+  pl->seg_cap = 0;
   if (pl->stream) cudaStreamDestroy(pl->stream);
   if (pl->s_in) cudaStreamDestroy(pl->s_in);
   if (pl->s_out) cudaStreamDestroy(pl->s_out);
-  for (cudaEvent_t e : pl->ev_in) cudaEventDestroy(e);
-  for (cudaEvent_t e : pl->ev_cmp) cudaEventDestroy(e);
-  for (kab_plan *c : pl->segs) plan_free(c);
+  pl->stream = nullptr; pl->s_in = nullptr; pl->s_out = nullptr;
+  pl->host_ready = false;
+}
+
+int plan_free(kab_plan *pl) {
+  if (!pl) return KAB_OK;
+  Trace tr("kab_plan_destroy");
+  DeviceGuard guard;
+  guard.enter(pl->device);
+  // pooled blocks may be handed to another plan at once, so nothing of this one may still be in
+  // flight (kab_plan_run_device is asynchronous): wait for the plan's own launches -- the events
+  // recorded behind them -- not for the device, which would stall the caller's unrelated streams
+  for (auto &se : pl->run_events) {
+    cudaEventSynchronize(se.second);
+    cudaEventDestroy(se.second);
+  }
+  pl->run_events.clear();
+  if (pl->stream) cudaStreamSynchronize(pl->stream);
+  if (pl->s_out) cudaStreamSynchronize(pl->s_out);
+  host_teardown(pl);
+  for (int q = 0; q < N_QUEUES; ++q) pool_free(pl->d_lists[q]);
+  pool_free(pl->d_col16); pool_free(pl->d_raw); pool_free(pl->d_bp); pool_free(pl->d_scratch);
+  pool_free(pl->d_queue); pool_free(pl->d_status_init); pool_free(pl->d_wide_ws); pool_free(pl->d_band_fifo); pool_free(pl->d_bt_meta); pool_free(pl->d_bt_maps); pool_free(pl->d_bt_entry); pool_free(pl->d_end_state); pool_free(pl->d_gather); pool_free(pl->d_lpc); pool_free(pl->d_nonfinite); pool_free(pl->d_t_off); pool_free(pl->d_seg_scratch);
   delete pl;
   tr.mark("free");
   return KAB_OK;
@@ -200,7 +287,8 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
     const int64_t T = t_off[b + 1] - t_off[b], L = l_off[b + 1] - l_off[b];
     if (T < 1 || T > 0x3fffffff || L < 0 || L > 0x3ffffff0) return KAB_E_BAD_ARG;
   }
-  KAB_CUDA(cudaSetDevice(device));
+  DeviceGuard guard;
+  KAB_CUDA(guard.enter(device));
   kab_plan *pl = new (std::nothrow) kab_plan();
   if (!pl) return KAB_E_NOMEM;
   pl->device = device; pl->B = B; pl->V = V; pl->W = W; pl->M = M;
@@ -255,7 +343,7 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
     const KabWideGeom wgeo = kab_wide_geom(pl->stage_bytes);
     int occ = 0;
     if (wgeo.smem_bytes <= 227 * 1024 &&
-        cudaFuncSetAttribute(kab_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wgeo.smem_bytes) == cudaSuccess &&
+        ensure_dyn_smem((const void *)kab_wide_kernel, device, wgeo.smem_bytes) == cudaSuccess &&
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kab_wide_kernel, KAB_WD_THREADS, wgeo.smem_bytes) == cudaSuccess)
       wide_capacity = occ * pl->sm_count;
     (void)cudaGetLastError();
@@ -433,7 +521,10 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
       rc = up((void **)&pl->d_lists[q], pl->lists[q].data(), pl->lists[q].size() * sizeof(KabLattice));
     if (rc) break;
     if ((rc = up((void **)&pl->d_col16, col16.data(), col16.size() * sizeof(uint16_t)))) break;
+    if (B > 0 && (rc = up((void **)&pl->d_t_off, t_off, (size_t)(B + 1) * sizeof(int64_t)))) break;
     if (pl->Vc) {
+      cudaError_t e3 = pool_malloc((void **)&pl->d_nonfinite, (size_t)B * sizeof(int32_t));
+      if (e3 != cudaSuccess) { rc = cuda_fail(e3, "pool_malloc(non-finite flags)"); break; }
       if ((rc = up((void **)&pl->d_gather, h_gather.data(), h_gather.size() * sizeof(int32_t)))) break;
       cudaError_t e2 = pool_malloc((void **)&pl->d_lpc, (size_t)pl->total_T * pl->Vc * sizeof(float));
       if (e2 != cudaSuccess) { rc = cuda_fail(e2, "pool_malloc(compact log-probs)"); break; }
@@ -451,7 +542,7 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
     if (!pl->lists[Q_WARP].empty()) {
       const size_t smem = 128 + (size_t)KAB_WARPS_PER_CTA * (KAB_WARP_STAGES * pl->stage_bytes + 256);  // + label tables
       const void *fn = Veff == 39 ? (const void *)kab_warp_kernel<39> : (const void *)kab_warp_kernel<0>;
-      if ((e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) { rc = cuda_fail(e, "cudaFuncSetAttribute(warp)"); break; }
+      if ((e = ensure_dyn_smem(fn, device, smem)) != cudaSuccess) { rc = cuda_fail(e, "cudaFuncSetAttribute(warp)"); break; }
       int occ = 0;
       if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, KAB_WARPS_PER_CTA * 32, smem)) != cudaSuccess) { rc = cuda_fail(e, "occupancy(warp)"); break; }
       pl->smem[Q_WARP] = smem;
@@ -472,7 +563,7 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
     if (!pl->lists[Q_BAND].empty() && pl->band_nc > 0) {
       if ((e = pool_malloc((void **)&pl->d_band_fifo, (size_t)pl->band_fifo_bytes)) != cudaSuccess) { rc = cuda_fail(e, "pool_malloc(band FIFOs)"); break; }
       const KabBandpGeom geo = kab_bandp_geom(pl->stage_bytes);
-      if ((e = cudaFuncSetAttribute(kab_bandp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)geo.smem_bytes)) != cudaSuccess) { rc = cuda_fail(e, "cudaFuncSetAttribute(bandp)"); break; }
+      if ((e = ensure_dyn_smem((const void *)kab_bandp_kernel, device, geo.smem_bytes)) != cudaSuccess) { rc = cuda_fail(e, "cudaFuncSetAttribute(bandp)"); break; }
       pl->smem[Q_BAND] = geo.smem_bytes;
       cudaLaunchConfig_t cfg{};
       cudaLaunchAttribute at[1];
@@ -489,7 +580,7 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
     } else if (!pl->lists[Q_BAND].empty()) {
       const KabBandGeom geo = kab_band_geom(pl->band_nw, pl->stage_bytes);
       const void *fn = pl->band_nw <= 16 ? (const void *)kab_band_kernel<512> : (const void *)kab_band_kernel<1024>;
-      if ((e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)geo.smem_bytes)) != cudaSuccess) { rc = cuda_fail(e, "cudaFuncSetAttribute(band)"); break; }
+      if ((e = ensure_dyn_smem(fn, device, geo.smem_bytes)) != cudaSuccess) { rc = cuda_fail(e, "cudaFuncSetAttribute(band)"); break; }
       int occ = 0;
       if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, pl->band_nw * 32, geo.smem_bytes)) != cudaSuccess) { rc = cuda_fail(e, "occupancy(band)"); break; }
       pl->smem[Q_BAND] = geo.smem_bytes;
@@ -533,7 +624,8 @@ int kab_plan_run_device(kab_plan *pl, const float *d_log_probs, int32_t *d_best_
   if (!d_log_probs || !d_best_path || !d_best_labels || !d_best_scores || !d_status) return KAB_E_BAD_ARG;
   if (reinterpret_cast<uintptr_t>(d_log_probs) & 15) return KAB_E_BAD_ARG;  // bulk copies need 16-byte alignment
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  KAB_CUDA(cudaSetDevice(pl->device));
+  DeviceGuard guard;
+  KAB_CUDA(guard.enter(pl->device));
   KabParams p{};
   p.lp = d_log_probs;
   p.lp_bytes = pl->total_T * (int64_t)pl->V * 4;
@@ -549,10 +641,12 @@ int kab_plan_run_device(kab_plan *pl, const float *d_log_probs, int32_t *d_best_
   KabParams pf = p;
   const int fast_lists[3] = {Q_WARP, Q_BAND, Q_WIDE};
   if (pl->Vc) {
+    KAB_CUDA(cudaMemsetAsync(pl->d_nonfinite, 0, (size_t)pl->B * sizeof(int32_t), stream));
     for (int q : fast_lists)
       if (!pl->lists[q].empty()) {
         const dim3 grid((unsigned)pl->lists[q].size(), (unsigned)((pl->max_T[q] + KAB_COMPACT_FRAMES - 1) / KAB_COMPACT_FRAMES));
-        kab_compact_kernel<<<grid, 256, 0, stream>>>(pl->d_lists[q], d_log_probs, pl->d_lpc, pl->d_gather, pl->V, pl->Vc);
+        kab_compact_kernel<<<grid, 256, 0, stream>>>(pl->d_lists[q], d_log_probs, pl->d_lpc, pl->d_gather, pl->V, pl->Vc,
+                                                     pl->d_nonfinite);
       }
     pf.lp = pl->d_lpc;
     pf.V = pl->Vc;
@@ -680,7 +774,8 @@ int kab_plan_run_device(kab_plan *pl, const float *d_log_probs, int32_t *d_best_
     for (int q : fast_lists)
       if (!pl->lists[q].empty()) {
         const dim3 grid((unsigned)pl->lists[q].size(), (unsigned)((pl->max_T[q] + KAB_COMPACT_FRAMES - 1) / KAB_COMPACT_FRAMES));
-        kab_expand_labels_kernel<<<grid, 64, 0, stream>>>(pl->d_lists[q], d_best_labels, d_status, pl->d_gather, pl->Vc);
+        kab_expand_labels_kernel<<<grid, 64, 0, stream>>>(pl->d_lists[q], d_best_labels, d_status, d_final_score,
+                                                          pl->d_gather, pl->Vc, pl->d_nonfinite);
       }
   if (!pl->lists[Q_GENERIC].empty()) {
     KabParams pg = p; pg.queue = pl->d_queue + Q_GENERIC;
@@ -688,7 +783,7 @@ int kab_plan_run_device(kab_plan *pl, const float *d_log_probs, int32_t *d_best_
         pl->d_lists[Q_GENERIC], (int)pl->lists[Q_GENERIC].size(), pg);
   }
   KAB_CUDA(cudaGetLastError());
-  return KAB_OK;
+  return record_run_event(pl, stream);
 }
 
 int kab_log_softmax_device(const float *d_logits, float *d_log_probs, int64_t n_rows, int32_t V, void *stream_) {
@@ -711,21 +806,21 @@ int kab_log_softmax_device(const float *d_logits, float *d_log_probs, int64_t n_
       const int64_t n_full = n_rows / KAB_SM_ROWS;
       if (n_full > 0) {
         const size_t smem_t = 128 + (size_t)KAB_SMT_BUFS * KAB_SM_ROWS * 39 * sizeof(float);
-        KAB_CUDA(cudaFuncSetAttribute(kab_log_softmax_tma_kernel<39>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+        KAB_CUDA(ensure_dyn_smem((const void *)kab_log_softmax_tma_kernel<39>, dev, smem_t));
         kab_log_softmax_tma_kernel<39><<<(unsigned)std::min<int64_t>(n_full, sms), KAB_SM_ROWS, smem_t, stream>>>(
             d_logits, d_log_probs, n_full);
       }
       const int64_t tail = n_rows - n_full * KAB_SM_ROWS;
       if (tail > 0) {
-        KAB_CUDA(cudaFuncSetAttribute(kab_log_softmax_kernel<39>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        KAB_CUDA(ensure_dyn_smem((const void *)kab_log_softmax_kernel<39>, dev, smem));
         kab_log_softmax_kernel<39><<<1, KAB_SM_ROWS, smem, stream>>>(d_logits + n_full * KAB_SM_ROWS * 39,
                                                                       d_log_probs + n_full * KAB_SM_ROWS * 39, tail, V, 1);
       }
     } else if (V == 39) {
-      KAB_CUDA(cudaFuncSetAttribute(kab_log_softmax_kernel<39>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      KAB_CUDA(ensure_dyn_smem((const void *)kab_log_softmax_kernel<39>, dev, smem));
       kab_log_softmax_kernel<39><<<grid, KAB_SM_ROWS, smem, stream>>>(d_logits, d_log_probs, n_rows, V, vec_ok);
     } else {
-      KAB_CUDA(cudaFuncSetAttribute(kab_log_softmax_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      KAB_CUDA(ensure_dyn_smem((const void *)kab_log_softmax_kernel<0>, dev, smem));
       kab_log_softmax_kernel<0><<<grid, KAB_SM_ROWS, smem, stream>>>(d_logits, d_log_probs, n_rows, V, vec_ok);
     }
   } else {
@@ -736,79 +831,217 @@ int kab_log_softmax_device(const float *d_logits, float *d_log_probs, int64_t n_
   return KAB_OK;
 }
 
-static int run_host_impl(kab_plan *pl, const float *h_log_probs, int32_t *h_best_path, int32_t *h_best_labels,
-                         float *h_best_scores, float *h_final_score, int32_t *h_status, bool logits,
-                         float *h_lp_out) {
-  if (!pl) return KAB_E_BAD_ARG;
-  if (pl->B == 0) return KAB_OK;
-  if (!h_log_probs || !h_best_path || !h_best_labels || !h_best_scores || !h_status) return KAB_E_BAD_ARG;
-  KAB_CUDA(cudaSetDevice(pl->device));
-  Trace tr("kab_plan_run_host");
+int kab_log_softmax_pack_device(const float *d_logits_tbv, int64_t t_max, int64_t n_seq, int32_t V,
+                                const int64_t *d_out_off, float *d_log_probs, int64_t n_rows, void *stream_) {
+  if (t_max < 0 || n_seq < 0 || n_rows < 0 || V < 1 || V > KAB_SM_MAX_V) return KAB_E_BAD_ARG;
+  if (n_rows == 0) return KAB_OK;
+  if (!d_logits_tbv || !d_out_off || !d_log_probs || n_seq == 0) return KAB_E_BAD_ARG;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int dev = 0, sms = 0;
+  KAB_CUDA(cudaGetDevice(&dev));
+  KAB_CUDA(sm_count_of(dev, &sms) == KAB_OK ? cudaSuccess : cudaErrorUnknown);
+  const size_t smem = (size_t)KAB_SM_ROWS * (V | 1) * sizeof(float);
+  const int64_t n_tiles = (n_rows + KAB_SM_ROWS - 1) / KAB_SM_ROWS;
+  const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / (smem + 4096)));
+  const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, (int64_t)sms * per_sm);
+  if (V == 39) {
+    KAB_CUDA(ensure_dyn_smem((const void *)kab_log_softmax_pack_kernel<39>, dev, smem));
+    kab_log_softmax_pack_kernel<39><<<grid, KAB_SM_ROWS, smem, stream>>>(d_logits_tbv, n_seq, d_out_off, d_log_probs, n_rows, V);
+  } else {
+    KAB_CUDA(ensure_dyn_smem((const void *)kab_log_softmax_pack_kernel<0>, dev, smem));
+    kab_log_softmax_pack_kernel<0><<<grid, KAB_SM_ROWS, smem, stream>>>(d_logits_tbv, n_seq, d_out_off, d_log_probs, n_rows, V);
+  }
+  KAB_CUDA(cudaGetLastError());
+  return KAB_OK;
+}
+
+// segment statistics of arrays already on the device (kab_segstats.cuh); asynchronous on `stream`
+static int segment_stats_launch(kab_plan *pl, const int32_t *d_path, const int32_t *d_lab, const float *d_sc,
+                                const int32_t *d_st, int64_t n_seg, const int64_t *d_seg_lat_off,
+                                const int64_t *d_seg_end, KabSegmentRecord *d_rec, uint8_t *d_lab8,
+                                cudaStream_t stream) {
+  if (n_seg > 0) {
+    if (!pl->d_seg_scratch) KAB_CUDA(pool_malloc((void **)&pl->d_seg_scratch, (size_t)std::max<int64_t>(pl->total_T, 1) * 4));
+    const unsigned grid = (unsigned)std::min<int64_t>((n_seg + KAB_SEG_WARPS - 1) / KAB_SEG_WARPS, (int64_t)pl->sm_count * 8);
+    kab_segment_stats_kernel<<<grid, KAB_SEG_WARPS * 32, 0, stream>>>(n_seg, pl->B, d_seg_lat_off, d_seg_end, pl->d_t_off,
+                                                                      d_path, d_lab, d_sc, d_st, pl->d_seg_scratch, d_rec);
+  }
+  if (d_lab8 && pl->total_T > 0) {
+    const unsigned grid = (unsigned)std::min<int64_t>((pl->total_T + 1023) / 1024, (int64_t)pl->sm_count * 8);
+    kab_labels_u8_kernel<<<grid, 256, 0, stream>>>(d_lab, d_lab8, pl->total_T);
+  }
+  KAB_CUDA(cudaGetLastError());
+  return record_run_event(pl, stream);
+}
+
+int kab_plan_segment_stats_device(kab_plan *pl, const int32_t *d_best_path, const int32_t *d_best_labels,
+                                  const float *d_best_scores, const int32_t *d_status, int64_t n_segments,
+                                  const int64_t *d_seg_lat_off, const int64_t *d_seg_end,
+                                  kab_segment_record *d_records, uint8_t *d_labels_u8, void *stream_) {
+  if (!pl || n_segments < 0) return KAB_E_BAD_ARG;
+  if (pl->B == 0) return n_segments == 0 ? KAB_OK : KAB_E_BAD_ARG;
+  if (!d_best_path || !d_best_labels || !d_best_scores || !d_status) return KAB_E_BAD_ARG;
+  if (n_segments > 0 && (!d_seg_lat_off || !d_seg_end || !d_records)) return KAB_E_BAD_ARG;
+  static_assert(sizeof(kab_segment_record) == sizeof(KabSegmentRecord), "record layout");
+  DeviceGuard guard;
+  KAB_CUDA(guard.enter(pl->device));
+  return segment_stats_launch(pl, d_best_path, d_best_labels, d_best_scores, d_status, n_segments, d_seg_lat_off,
+                              d_seg_end, reinterpret_cast<KabSegmentRecord *>(d_records), d_labels_u8,
+                              reinterpret_cast<cudaStream_t>(stream_));
+}
+
+namespace {
+
+struct HostRun {  // what one kab_plan_run_host* call asks for
+  const float *h_in = nullptr;  // log-probs, or raw logits when `logits`
+  bool logits = false;
+  float *h_lp_out = nullptr;
+  int32_t *h_path = nullptr, *h_lab = nullptr, *h_status = nullptr;
+  float *h_sc = nullptr, *h_fs = nullptr;
+  // segment records (optional)
+  int64_t n_seg = 0;
+  const int64_t *h_seg_lat_off = nullptr, *h_seg_end = nullptr;
+  kab_segment_record *h_rec = nullptr;
+  uint8_t *h_lab8 = nullptr;
+};
+
+// Streams, device buffers and -- for large batches -- the child plans of the pipelined path.  Built
+// into the plan only as a whole: any failure tears everything down again (host_teardown), so a later
+// call starts from scratch instead of running over a half-built set of segments.
+int host_setup(kab_plan *pl) {
+  if (pl->host_ready) return KAB_OK;
   const size_t n = (size_t)pl->total_T, B = (size_t)pl->B;
   const int64_t V = pl->V;
-  if (!pl->stream) {
-    KAB_CUDA(cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking));
-    KAB_CUDA(cudaStreamCreateWithFlags(&pl->s_in, cudaStreamNonBlocking));
-    KAB_CUDA(cudaStreamCreateWithFlags(&pl->s_out, cudaStreamNonBlocking));
-    KAB_CUDA(pool_malloc((void **)&pl->d_lp, n * V * 4));
-    KAB_CUDA(pool_malloc((void **)&pl->d_path, n * 4));
-    KAB_CUDA(pool_malloc((void **)&pl->d_lab, n * 4));
-    KAB_CUDA(pool_malloc((void **)&pl->d_sc, n * 4));
-    KAB_CUDA(pool_malloc((void **)&pl->d_fs, B * 4));
-    KAB_CUDA(pool_malloc((void **)&pl->d_st, B * 4));
-    // ---- cut the batch into segments of >= 32 MB of log-probs, at lattice boundaries whose
-    // first row is 16-byte aligned (bulk copies), at most 12 segments
-    const int64_t bytes_total = (int64_t)n * V * 4;
-    // (only worthwhile when every segment still holds enough lattices to fill the GPU: a few
-    // long chapters are better off in one launch, where they run side by side)
-    int want = (int)std::min<int64_t>(std::min<int64_t>(12, bytes_total / (32ll << 20)), (int64_t)B / 512);
-    if (want >= 2 && pl->h_t_off[0] == 0) {
-      std::vector<int64_t> cuts{0};
-      for (int k = 1; k < want; ++k) {
-        const int64_t target = (int64_t)n * k / want;
-        int64_t b = std::lower_bound(pl->h_t_off.begin(), pl->h_t_off.end(), target) - pl->h_t_off.begin();
-        while (b < (int64_t)B && (pl->h_t_off[b] * V) % 4 != 0) ++b;
-        if (b > cuts.back() && b < (int64_t)B) cuts.push_back(b);
-      }
-      if (cuts.size() >= 2) {
-        cuts.push_back((int64_t)B);
-        for (size_t k = 0; k + 1 < cuts.size(); ++k) {
-          const int64_t b0 = cuts[k], b1 = cuts[k + 1];
-          std::vector<int64_t> to(pl->h_t_off.begin() + b0, pl->h_t_off.begin() + b1 + 1);
-          std::vector<int64_t> lo(pl->h_l_off.begin() + b0, pl->h_l_off.begin() + b1 + 1);
-          const int64_t t0 = to[0], l0 = lo[0];
-          for (auto &x : to) x -= t0;
-          for (auto &x : lo) x -= l0;
-          kab_plan *c = nullptr;
-          const int32_t *lab = pl->h_labels.empty() ? nullptr : pl->h_labels.data() + l0;
-          int rc = kab_plan_create(&c, pl->device, b1 - b0, to.data(), lab, lo.data(), pl->V, pl->W, pl->M);
-          if (rc != KAB_OK) return rc;
-          c->is_child = true;
-          pl->segs.push_back(c);
-          pl->seg_b0.push_back(b0);
-          cudaEvent_t e1, e2;
-          KAB_CUDA(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
-          KAB_CUDA(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
-          pl->ev_in.push_back(e1);
-          pl->ev_cmp.push_back(e2);
-        }
+  auto fail = [&](int rc) { host_teardown(pl); return rc; };
+#define KAB_SETUP(call)                                                  \
+  do {                                                                   \
+    cudaError_t e_ = (call);                                             \
+    if (e_ != cudaSuccess) return fail(cuda_fail(e_, #call));            \
+  } while (0)
+  KAB_SETUP(cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking));
+  KAB_SETUP(cudaStreamCreateWithFlags(&pl->s_in, cudaStreamNonBlocking));
+  KAB_SETUP(cudaStreamCreateWithFlags(&pl->s_out, cudaStreamNonBlocking));
+  KAB_SETUP(pool_malloc((void **)&pl->d_lp, n * V * 4));
+  KAB_SETUP(pool_malloc((void **)&pl->d_path, n * 4));
+  KAB_SETUP(pool_malloc((void **)&pl->d_lab, n * 4));
+  KAB_SETUP(pool_malloc((void **)&pl->d_sc, n * 4));
+  KAB_SETUP(pool_malloc((void **)&pl->d_fs, B * 4));
+  KAB_SETUP(pool_malloc((void **)&pl->d_st, B * 4));
+  // ---- cut the batch into segments of >= 32 MB of log-probs, at lattice boundaries whose
+  // first row is 16-byte aligned (bulk copies), at most 12 segments
+  const int64_t bytes_total = (int64_t)n * V * 4;
+  // (only worthwhile when every segment still holds enough lattices to fill the GPU: a few
+  // long chapters are better off in one launch, where they run side by side)
+  int want = (int)std::min<int64_t>(std::min<int64_t>(12, bytes_total / (32ll << 20)), (int64_t)B / 512);
+  if (const char *fs = getenv("KAB_HOST_SEGMENTS")) want = atoi(fs);  // development / tests
+  if (want >= 2 && pl->h_t_off[0] == 0) {
+    std::vector<int64_t> cuts{0};
+    for (int k = 1; k < want; ++k) {
+      const int64_t target = (int64_t)n * k / want;
+      int64_t b = std::lower_bound(pl->h_t_off.begin(), pl->h_t_off.end(), target) - pl->h_t_off.begin();
+      while (b < (int64_t)B && (pl->h_t_off[b] * V) % 4 != 0) ++b;
+      if (b > cuts.back() && b < (int64_t)B) cuts.push_back(b);
+    }
+    if (cuts.size() >= 2) {
+      cuts.push_back((int64_t)B);
+      const char *inject = getenv("KAB_TEST_FAIL_CHILD");  // tests: make the k-th child plan fail
+      for (size_t k = 0; k + 1 < cuts.size(); ++k) {
+        const int64_t b0 = cuts[k], b1 = cuts[k + 1];
+        std::vector<int64_t> to(pl->h_t_off.begin() + b0, pl->h_t_off.begin() + b1 + 1);
+        std::vector<int64_t> lo(pl->h_l_off.begin() + b0, pl->h_l_off.begin() + b1 + 1);
+        const int64_t t0 = to[0], l0 = lo[0];
+        for (auto &x : to) x -= t0;
+        for (auto &x : lo) x -= l0;
+        kab_plan *c = nullptr;
+        const int32_t *lab = pl->h_labels.empty() ? nullptr : pl->h_labels.data() + l0;
+        int rc = (inject && atoi(inject) == (int)k) ? KAB_E_NOMEM
+                                                     : kab_plan_create(&c, pl->device, b1 - b0, to.data(), lab, lo.data(), pl->V, pl->W, pl->M);
+        if (rc != KAB_OK) return fail(rc);
+        c->is_child = true;
+        pl->segs.push_back(c);
+        pl->seg_b0.push_back(b0);
+        cudaEvent_t e1 = nullptr, e2 = nullptr;
+        KAB_SETUP(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+        pl->ev_in.push_back(e1);
+        KAB_SETUP(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+        pl->ev_cmp.push_back(e2);
       }
     }
   }
+#undef KAB_SETUP
+  pl->host_ready = true;
+  return KAB_OK;
+}
+
+int run_host_impl(kab_plan *pl, const HostRun &r) {
+  if (!pl) return KAB_E_BAD_ARG;
+  if (pl->B == 0) return r.n_seg == 0 ? KAB_OK : KAB_E_BAD_ARG;
+  if (!r.h_in || !r.h_status) return KAB_E_BAD_ARG;
+  const bool arrays = r.h_path || r.h_lab || r.h_sc;
+  if (arrays && (!r.h_path || !r.h_lab || !r.h_sc)) return KAB_E_BAD_ARG;
+  if (!arrays && !r.h_rec && !r.h_lab8) return KAB_E_BAD_ARG;  // nothing requested
+  if (r.n_seg < 0 || (r.n_seg > 0 && (!r.h_seg_lat_off || !r.h_seg_end || !r.h_rec))) return KAB_E_BAD_ARG;
+  if (r.n_seg > 0) {  // the reference's `indices`: cumulative ends per lattice, non-decreasing, >= 0
+    if (r.h_seg_lat_off[0] != 0 || r.h_seg_lat_off[pl->B] != r.n_seg) return KAB_E_BAD_ARG;
+    for (int64_t b = 0; b < pl->B; ++b) {
+      if (r.h_seg_lat_off[b + 1] < r.h_seg_lat_off[b]) return KAB_E_BAD_ARG;
+      int64_t prev = 0;
+      for (int64_t k = r.h_seg_lat_off[b]; k < r.h_seg_lat_off[b + 1]; ++k) {
+        if (r.h_seg_end[k] < prev) return KAB_E_BAD_ARG;
+        prev = r.h_seg_end[k];
+      }
+    }
+  }
+  DeviceGuard guard;
+  KAB_CUDA(guard.enter(pl->device));
+  Trace tr("kab_plan_run_host");
+  const size_t n = (size_t)pl->total_T, B = (size_t)pl->B;
+  const int64_t V = pl->V;
+  if (int rc = host_setup(pl)) return rc;
+  const bool want_stats = r.n_seg > 0 || r.h_lab8;
+  if (want_stats) {
+    const int64_t need = (int64_t)B + 1 + r.n_seg;
+    if (need > pl->seg_cap) {
+      pool_free(pl->d_seg_off); pool_free(pl->d_seg_rec);
+      pl->d_seg_off = nullptr; pl->d_seg_rec = nullptr; pl->seg_cap = 0;
+      KAB_CUDA(pool_malloc((void **)&pl->d_seg_off, (size_t)need * 8));
+      KAB_CUDA(pool_malloc((void **)&pl->d_seg_rec, (size_t)std::max<int64_t>(r.n_seg, 1) * sizeof(KabSegmentRecord)));
+      pl->seg_cap = need;
+    }
+    if (r.h_lab8 && !pl->d_lab8) KAB_CUDA(pool_malloc((void **)&pl->d_lab8, std::max<size_t>(n, 1)));
+    if (r.n_seg > 0) {  // (on the compute stream, where the statistics kernel runs)
+      KAB_CUDA(cudaMemcpyAsync(pl->d_seg_off, r.h_seg_lat_off, (B + 1) * 8, cudaMemcpyHostToDevice, pl->stream));
+      KAB_CUDA(cudaMemcpyAsync(pl->d_seg_off + B + 1, r.h_seg_end, (size_t)r.n_seg * 8, cudaMemcpyHostToDevice, pl->stream));
+    }
+  }
   tr.mark("streams, buffers, segments");
+  // results that leave after the alignment of the whole batch (stream s): segment records, byte labels
+  auto finish = [&](cudaStream_t s) -> int {
+    if (!want_stats) return KAB_OK;
+    int rc = segment_stats_launch(pl, pl->d_path, pl->d_lab, pl->d_sc, pl->d_st, r.n_seg, pl->d_seg_off,
+                                  pl->d_seg_off + B + 1, pl->d_seg_rec, r.h_lab8 ? pl->d_lab8 : nullptr, s);
+    if (rc != KAB_OK) return rc;
+    if (r.n_seg > 0)
+      KAB_CUDA(cudaMemcpyAsync(r.h_rec, pl->d_seg_rec, (size_t)r.n_seg * sizeof(KabSegmentRecord), cudaMemcpyDeviceToHost, s));
+    if (r.h_lab8) KAB_CUDA(cudaMemcpyAsync(r.h_lab8, pl->d_lab8, n, cudaMemcpyDeviceToHost, s));
+    return KAB_OK;
+  };
   if (pl->segs.empty()) {  // small batch: one copy in, one run, one copy out
     cudaStream_t s = pl->stream;
-    KAB_CUDA(cudaMemcpyAsync(pl->d_lp, h_log_probs, n * V * 4, cudaMemcpyHostToDevice, s));
+    KAB_CUDA(cudaMemcpyAsync(pl->d_lp, r.h_in, n * V * 4, cudaMemcpyHostToDevice, s));
     int rc = KAB_OK;
-    if (logits && (rc = kab_log_softmax_device(pl->d_lp, pl->d_lp, (int64_t)n, pl->V, s)) != KAB_OK) return rc;
+    if (r.logits && (rc = kab_log_softmax_device(pl->d_lp, pl->d_lp, (int64_t)n, pl->V, s)) != KAB_OK) return rc;
     rc = kab_plan_run_device(pl, pl->d_lp, pl->d_path, pl->d_lab, pl->d_sc, pl->d_fs, pl->d_st, s);
     if (rc != KAB_OK) return rc;
-    if (h_lp_out) KAB_CUDA(cudaMemcpyAsync(h_lp_out, pl->d_lp, n * V * 4, cudaMemcpyDeviceToHost, s));
-    KAB_CUDA(cudaMemcpyAsync(h_best_path, pl->d_path, n * 4, cudaMemcpyDeviceToHost, s));
-    KAB_CUDA(cudaMemcpyAsync(h_best_labels, pl->d_lab, n * 4, cudaMemcpyDeviceToHost, s));
-    KAB_CUDA(cudaMemcpyAsync(h_best_scores, pl->d_sc, n * 4, cudaMemcpyDeviceToHost, s));
-    if (h_final_score) KAB_CUDA(cudaMemcpyAsync(h_final_score, pl->d_fs, B * 4, cudaMemcpyDeviceToHost, s));
-    KAB_CUDA(cudaMemcpyAsync(h_status, pl->d_st, B * 4, cudaMemcpyDeviceToHost, s));
+    if (r.h_lp_out) KAB_CUDA(cudaMemcpyAsync(r.h_lp_out, pl->d_lp, n * V * 4, cudaMemcpyDeviceToHost, s));
+    if (arrays) {
+      KAB_CUDA(cudaMemcpyAsync(r.h_path, pl->d_path, n * 4, cudaMemcpyDeviceToHost, s));
+      KAB_CUDA(cudaMemcpyAsync(r.h_lab, pl->d_lab, n * 4, cudaMemcpyDeviceToHost, s));
+      KAB_CUDA(cudaMemcpyAsync(r.h_sc, pl->d_sc, n * 4, cudaMemcpyDeviceToHost, s));
+    }
+    if (r.h_fs) KAB_CUDA(cudaMemcpyAsync(r.h_fs, pl->d_fs, B * 4, cudaMemcpyDeviceToHost, s));
+    KAB_CUDA(cudaMemcpyAsync(r.h_status, pl->d_st, B * 4, cudaMemcpyDeviceToHost, s));
+    if ((rc = finish(s)) != KAB_OK) return rc;
     tr.mark("enqueue");
     KAB_CUDA(cudaStreamSynchronize(s));
     tr.mark("synchronize");
@@ -819,41 +1052,67 @@ static int run_host_impl(kab_plan *pl, const float *h_log_probs, int32_t *h_best
     kab_plan *c = pl->segs[k];
     const size_t b0 = (size_t)pl->seg_b0[k], t0 = (size_t)pl->h_t_off[b0];
     const size_t nk = (size_t)c->total_T, bk = (size_t)c->B;
-    KAB_CUDA(cudaMemcpyAsync(pl->d_lp + t0 * V, h_log_probs + t0 * V, nk * V * 4, cudaMemcpyHostToDevice, pl->s_in));
+    KAB_CUDA(cudaMemcpyAsync(pl->d_lp + t0 * V, r.h_in + t0 * V, nk * V * 4, cudaMemcpyHostToDevice, pl->s_in));
     KAB_CUDA(cudaEventRecord(pl->ev_in[k], pl->s_in));
     KAB_CUDA(cudaStreamWaitEvent(pl->stream, pl->ev_in[k], 0));
     int rc = KAB_OK;
-    if (logits && (rc = kab_log_softmax_device(pl->d_lp + t0 * V, pl->d_lp + t0 * V, (int64_t)nk, pl->V, pl->stream)) != KAB_OK)
+    if (r.logits && (rc = kab_log_softmax_device(pl->d_lp + t0 * V, pl->d_lp + t0 * V, (int64_t)nk, pl->V, pl->stream)) != KAB_OK)
       return rc;
     rc = kab_plan_run_device(c, pl->d_lp + t0 * V, pl->d_path + t0, pl->d_lab + t0, pl->d_sc + t0,
                              pl->d_fs + b0, pl->d_st + b0, pl->stream);
     if (rc != KAB_OK) return rc;
     KAB_CUDA(cudaEventRecord(pl->ev_cmp[k], pl->stream));
     KAB_CUDA(cudaStreamWaitEvent(pl->s_out, pl->ev_cmp[k], 0));
-    if (h_lp_out)
-      KAB_CUDA(cudaMemcpyAsync(h_lp_out + t0 * V, pl->d_lp + t0 * V, nk * V * 4, cudaMemcpyDeviceToHost, pl->s_out));
-    KAB_CUDA(cudaMemcpyAsync(h_best_path + t0, pl->d_path + t0, nk * 4, cudaMemcpyDeviceToHost, pl->s_out));
-    KAB_CUDA(cudaMemcpyAsync(h_best_labels + t0, pl->d_lab + t0, nk * 4, cudaMemcpyDeviceToHost, pl->s_out));
-    KAB_CUDA(cudaMemcpyAsync(h_best_scores + t0, pl->d_sc + t0, nk * 4, cudaMemcpyDeviceToHost, pl->s_out));
-    if (h_final_score)
-      KAB_CUDA(cudaMemcpyAsync(h_final_score + b0, pl->d_fs + b0, bk * 4, cudaMemcpyDeviceToHost, pl->s_out));
-    KAB_CUDA(cudaMemcpyAsync(h_status + b0, pl->d_st + b0, bk * 4, cudaMemcpyDeviceToHost, pl->s_out));
+    if (r.h_lp_out)
+      KAB_CUDA(cudaMemcpyAsync(r.h_lp_out + t0 * V, pl->d_lp + t0 * V, nk * V * 4, cudaMemcpyDeviceToHost, pl->s_out));
+    if (arrays) {
+      KAB_CUDA(cudaMemcpyAsync(r.h_path + t0, pl->d_path + t0, nk * 4, cudaMemcpyDeviceToHost, pl->s_out));
+      KAB_CUDA(cudaMemcpyAsync(r.h_lab + t0, pl->d_lab + t0, nk * 4, cudaMemcpyDeviceToHost, pl->s_out));
+      KAB_CUDA(cudaMemcpyAsync(r.h_sc + t0, pl->d_sc + t0, nk * 4, cudaMemcpyDeviceToHost, pl->s_out));
+    }
+    if (r.h_fs)
+      KAB_CUDA(cudaMemcpyAsync(r.h_fs + b0, pl->d_fs + b0, bk * 4, cudaMemcpyDeviceToHost, pl->s_out));
+    KAB_CUDA(cudaMemcpyAsync(r.h_status + b0, pl->d_st + b0, bk * 4, cudaMemcpyDeviceToHost, pl->s_out));
   }
+  if (int rc = finish(pl->stream)) return rc;
   KAB_CUDA(cudaStreamSynchronize(pl->s_out));
   KAB_CUDA(cudaStreamSynchronize(pl->stream));
   return KAB_OK;
 }
 
+}  // namespace
+
 int kab_plan_run_host(kab_plan *pl, const float *h_log_probs, int32_t *h_best_path, int32_t *h_best_labels,
                       float *h_best_scores, float *h_final_score, int32_t *h_status) {
-  return run_host_impl(pl, h_log_probs, h_best_path, h_best_labels, h_best_scores, h_final_score, h_status, false,
-                       nullptr);
+  if (!h_best_path || !h_best_labels || !h_best_scores) return pl && pl->B == 0 ? KAB_OK : KAB_E_BAD_ARG;
+  HostRun r;
+  r.h_in = h_log_probs; r.h_path = h_best_path; r.h_lab = h_best_labels; r.h_sc = h_best_scores;
+  r.h_fs = h_final_score; r.h_status = h_status;
+  return run_host_impl(pl, r);
 }
 
 int kab_plan_run_host_logits(kab_plan *pl, const float *h_logits, int32_t *h_best_path, int32_t *h_best_labels,
                              float *h_best_scores, float *h_final_score, int32_t *h_status, float *h_log_probs) {
-  return run_host_impl(pl, h_logits, h_best_path, h_best_labels, h_best_scores, h_final_score, h_status, true,
-                       h_log_probs);
+  if (!h_best_path || !h_best_labels || !h_best_scores) return pl && pl->B == 0 ? KAB_OK : KAB_E_BAD_ARG;
+  HostRun r;
+  r.h_in = h_logits; r.logits = true; r.h_lp_out = h_log_probs;
+  r.h_path = h_best_path; r.h_lab = h_best_labels; r.h_sc = h_best_scores;
+  r.h_fs = h_final_score; r.h_status = h_status;
+  return run_host_impl(pl, r);
+}
+
+int kab_plan_run_host_segments(kab_plan *pl, const float *h_in, int32_t is_logits, int64_t n_segments,
+                               const int64_t *h_seg_lat_off, const int64_t *h_seg_end,
+                               kab_segment_record *h_records, uint8_t *h_labels_u8, int32_t *h_best_path,
+                               int32_t *h_best_labels, float *h_best_scores, float *h_final_score,
+                               int32_t *h_status) {
+  HostRun r;
+  r.h_in = h_in; r.logits = is_logits != 0;
+  r.n_seg = n_segments; r.h_seg_lat_off = h_seg_lat_off; r.h_seg_end = h_seg_end; r.h_rec = h_records;
+  r.h_lab8 = h_labels_u8;
+  r.h_path = h_best_path; r.h_lab = h_best_labels; r.h_sc = h_best_scores;
+  r.h_fs = h_final_score; r.h_status = h_status;
+  return run_host_impl(pl, r);
 }
 
 int kab_ctc_best_path(const float *log_probs, int64_t T, int32_t V, const int32_t *labels, int64_t L,

@@ -120,12 +120,24 @@ __host__ __device__ inline size_t kab_bandp_fifo_off(int nwt) { return ((size_t)
 __host__ __device__ inline size_t kab_bandp_ws_bytes(int nwt) {
   return kab_bandp_fifo_off(nwt) + (size_t)nwt * KAB_BP_D * KAB_BP_MSG_BYTES;
 }
+// (score, seq) travel as ONE 64-bit access: PTX guarantees single-copy atomicity for a naturally
+// aligned .b64 access, not for a .v2.b32 vector (which the memory model treats as two accesses).
 __device__ __forceinline__ void kab_st_volatile_b64(void *p, uint32_t lo, uint32_t hi) {
-  asm volatile("st.relaxed.gpu.global.v2.b32 [%0], {%1, %2};" ::"l"(p), "r"(lo), "r"(hi) : "memory");
+  asm volatile(
+      "{\n\t.reg .b64 q;\n\t"
+      "mov.b64 q, {%1, %2};\n\t"
+      "st.relaxed.gpu.global.b64 [%0], q;\n\t}" ::"l"(p), "r"(lo), "r"(hi)
+      : "memory");
 }
 __device__ __forceinline__ uint2 kab_ld_volatile_b64(const void *p) {
   uint2 v;
-  asm volatile("ld.relaxed.gpu.global.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+  asm volatile(
+      "{\n\t.reg .b64 q;\n\t"
+      "ld.relaxed.gpu.global.b64 q, [%2];\n\t"
+      "mov.b64 {%0, %1}, q;\n\t}"
+      : "=r"(v.x), "=r"(v.y)
+      : "l"(p)
+      : "memory");
   return v;
 }
 __device__ __forceinline__ uint32_t kab_ld_volatile_u32(const void *p) {

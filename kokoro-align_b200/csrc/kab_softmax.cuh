@@ -186,6 +186,58 @@ kab_log_softmax_kernel(const float *in, float *out, int64_t n_rows, int V_rt, in
   }
 }
 
+// The hand-off from the acoustic model: predict() (train.py:215-229) gets a
+// padded, time-major batch `logits [T_max, B, V]` + `lens [B]` from the encoder and appends
+// logits[:len_j, j, :] of every segment j to the chapter's *.logits.npz.  This kernel does that
+// append and align.py:116-117 in one pass, device to device: output row out_off[j] + t (the packed
+// chapter rows) = log_softmax(logits[t, j, :]).  Same arithmetic as kab_log_softmax_kernel; a CTA
+// takes a tile of KAB_SM_ROWS OUTPUT rows (contiguous stores), the loads are whole 4 V-byte rows.
+template <int VT>
+__global__ void __launch_bounds__(KAB_SM_ROWS)
+kab_log_softmax_pack_kernel(const float *__restrict__ in, int64_t B, const int64_t *__restrict__ out_off,
+                            float *__restrict__ out, int64_t n_rows, int V_rt) {
+  extern __shared__ __align__(16) float kab_sm_tile[];
+  __shared__ const float *srow[KAB_SM_ROWS];
+  const int V = VT > 0 ? VT : V_rt;
+  const int VS = V | 1;
+  const int64_t n_tiles = (n_rows + KAB_SM_ROWS - 1) / KAB_SM_ROWS;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t r0 = tile * KAB_SM_ROWS;
+    const int rows = (int)min((int64_t)KAB_SM_ROWS, n_rows - r0);
+    if ((int)threadIdx.x < rows) {  // source row of output row r: segment j = last one with out_off[j] <= r
+      const int64_t r = r0 + threadIdx.x;
+      int64_t lo = 0, hi = B;
+      while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (out_off[mid] <= r) lo = mid; else hi = mid;
+      }
+      srow[threadIdx.x] = in + ((r - out_off[lo]) * B + lo) * V;
+    }
+    __syncthreads();
+    const int n_el = rows * V;
+    for (int e = threadIdx.x; e < n_el; e += KAB_SM_ROWS) {
+      const int rr = e / V, c = e - rr * V;
+      kab_sm_tile[rr * VS + c] = __ldcs(srow[rr] + c);
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < rows) {
+      float *x = kab_sm_tile + threadIdx.x * VS;
+      const float mean = __fdiv_rn(kab_np_rowsum(V, [&](int i) { return x[i]; }), (float)V);
+      const float se = kab_np_rowsum(V, [&](int i) {
+        const float y = __fsub_rn(x[i], mean);
+        x[i] = y;
+        return expf(y);
+      });
+      const float lse = logf(se);
+      for (int i = 0; i < V; ++i) x[i] = __fsub_rn(x[i], lse);
+    }
+    __syncthreads();
+    float *dst = out + r0 * V;
+    for (int e = threadIdx.x; e < n_el; e += KAB_SM_ROWS) dst[e] = kab_sm_tile[(e / V) * VS + e % V];
+    __syncthreads();
+  }
+}
+
 // V > KAB_SM_MAX_V: a warp per row, lane-strided partial sums combined by a butterfly (the sums
 // are then NOT in numpy's order -- the same few-ulp tolerance applies)
 __global__ void __launch_bounds__(256)

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), f"{n} declared in the header but not exported"
     assert sorted(_lib.EXPORTS) == names
-    assert L.kab_version() == 100
+    assert L.kab_version() == 200
     assert L.kab_error_string(-2) == b"bad argument"
 
 

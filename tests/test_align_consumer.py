@@ -73,3 +73,38 @@ def test_file_level_pipeline_matches_reference(tmp_path):
         assert set(f.keys()) == {"best_path", "best_labels", "best_scores"}
         assert f["best_path"].dtype == np.int32 and f["best_scores"].dtype == np.float32
         assert len(f["best_path"]) == len(lp)
+
+
+def test_numpy_pairwise_sum_model():
+    """The summation order the segment-statistics kernel implements IS np.sum's (float32,
+    contiguous): checked on every length around the block / split boundaries."""
+    from tests.np_sum_model import pairwise_sum
+    rng = np.random.default_rng(7)
+    lengths = list(range(0, 300)) + [511, 512, 513, 1000, 1023, 1024, 1025, 2049, 4097, 10007]
+    for n in lengths:
+        a = (-rng.random(n) * 9).astype(np.float32)       # log-prob-like: negative, finite
+        assert np.float32(pairwise_sum(a)).tobytes() == np.float32(np.sum(a)).tobytes(), n
+        b = (a[a < -4.0]).copy()                           # a compacted copy, as scores[labels != 0]
+        assert np.float32(pairwise_sum(b)).tobytes() == np.float32(np.sum(b)).tobytes(), n
+
+
+def test_align_from_records_matches_reference_text(tmp_path):
+    """align_from_records (the writer fed by the device's segment records) against the reference's
+    text, with the records computed on the HOST from the golden arrays by the reference's own
+    expressions (align.py:151-162): pins the record contract without a GPU."""
+    from kokoro_align_b200 import align
+    with np.load(os.path.join(CASE, "case.best_path.npz")) as f:
+        path, labs, scores = f["best_path"], f["best_labels"], f["best_scores"]
+    with np.load(os.path.join(CASE, "case.mfcc.npz")) as f:
+        ends = f["indices"]
+    rec = np.zeros(len(ends), align.SEGMENT_RECORD)
+    for i in range(len(ends)):
+        a = int(ends[i - 1]) if i > 0 else 0
+        b = int(ends[i])
+        voiced = labs[a:b] != 0
+        rec[i] = (path[a] // 2, path[b] // 2 if b < len(path) else -1, np.sum(voiced),
+                  np.sum(scores[a:b][voiced]), np.sum(scores[a:b]), 0)
+    for rw in (True, False):
+        out = tmp_path / f"r{int(rw)}.align.txt"
+        align.align_from_records(rec, labs.astype(np.uint8), ends, os.path.join(CASE, "case.voca.txt"), str(out), rw)
+        assert out.read_text() == open(os.path.join(CASE, f"case.align.wordsep{int(not rw)}.txt")).read()

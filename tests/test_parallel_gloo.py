@@ -150,3 +150,75 @@ def test_cells_eval_matches_oracle():
     from oracle import ctc_oracle
     for T, L, W in ((81135, 11359, 1000), (861, 121, 1000), (100, 300, 20), (1500, 450, 1000), (1, 0, 5)):
         assert parallel.cells_eval(T, L, W) == ctc_oracle.cells_eval(T, L, W)
+
+
+def _late_rank_worker(rank, world, port, q, d, mode):
+    """mode 'late': rank 1 enters best_path_files after rank 0 has finished its own shard (its
+    outputs already exist when rank 1 would scan); mode 'error': rank 1's alignment raises;
+    mode 'nothing': every output exists."""
+    import time
+    import torch.distributed as dist
+    from kokoro_align_b200 import align
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n = 6
+    lf = [os.path.join(d, f"c{k}.logits.npz") for k in range(n)]
+    vf = [os.path.join(d, f"c{k}.voca.txt") for k in range(n)]
+    bf = [os.path.join(d, f"c{k}.best_path.npz") for k in range(n)]
+
+    def fn(*a):
+        if mode == "late" and rank == 1:
+            time.sleep(1.0)      # rank 0's files are on disk long before this rank is done
+        if mode == "error" and rank == 1:
+            raise align.KabError("injected failure on rank 1")
+        return _oracle_align(*a)
+    if mode == "late" and rank == 1:
+        time.sleep(0.5)
+    try:
+        written = align.best_path_files(lf, vf, bf, verbose=False, align_fn=fn)
+        q.put((rank, "ok", written))
+    except Exception as e:   # noqa: BLE001
+        q.put((rank, type(e).__name__, str(e)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode", ["late", "error", "nothing"])
+def test_best_path_files_world2_consistent_todo_and_errors(tmp_path, mode):
+    """The list of chapters to align is decided once (rank 0) and broadcast, so a rank that starts
+    late cannot see the other rank's fresh outputs and compute a different partition; an error on
+    one rank is raised on every rank AFTER the collective (nobody hangs); nothing to do returns []
+    on every rank."""
+    rng = np.random.default_rng(45)
+    d = str(tmp_path)
+    Ts = [400, 90, 700, 33, 500, 260]
+    for k, T in enumerate(Ts):
+        np.savez(os.path.join(d, f"c{k}.logits.npz"), data=(rng.standard_normal((T, 39)) * 3).astype(np.float32),
+                 indices=np.array([T], np.int32))
+        with open(os.path.join(d, f"c{k}.voca.txt"), "w") as f:
+            for _ in range(max(1, T // 60)):
+                f.write("t|k o k o r o\n")
+        if mode == "nothing":
+            np.savez(os.path.join(d, f"c{k}.best_path.npz"), best_path=np.zeros(1, np.int32))
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_late_rank_worker, args=(r, world, port, q, d, mode)) for r in range(world)]
+    for p in procs:
+        p.start()
+    outs = dict((o[0], o[1:]) for o in (q.get(timeout=120) for _ in range(world)))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    if mode == "late":
+        expect = [os.path.join(d, f"c{k}.best_path.npz") for k in range(6)]
+        assert outs[0] == ("ok", expect) and outs[1] == ("ok", [])
+        for k in range(6):   # every chapter aligned exactly once, by its own rank
+            with np.load(os.path.join(d, f"c{k}.best_path.npz")) as f:
+                assert len(f["best_path"]) == Ts[k]
+    elif mode == "error":
+        assert outs[0][0] == "KabError" and outs[1][0] == "KabError"
+        assert "injected failure" in outs[0][1]
+    else:
+        assert outs[0] == ("ok", []) and outs[1] == ("ok", [])
