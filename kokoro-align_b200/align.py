@@ -24,7 +24,11 @@ SEGMENT_RECORD = np.dtype([("text_start", "<i4"), ("text_end", "<i4"), ("non_bla
 
 def flat_segments(indices_list):
     """The reference's per-chapter ``indices`` arrays (cumulative segment ends, preprocess.py:12-35)
-    -> the C-ABI layout (seg_lat_off int64 [B+1], seg_end int64 [n_segments])."""
+    -> the C-ABI layout (seg_lat_off int64 [B+1], seg_end int64 [n_segments]).  A tuple is taken
+    to be that layout already (callers that run the same segmentation many times build it once)."""
+    if isinstance(indices_list, tuple):
+        seg_lat_off, seg_end = indices_list
+        return (np.ascontiguousarray(seg_lat_off, dtype=np.int64), np.ascontiguousarray(seg_end, dtype=np.int64))
     seg_lat_off = np.concatenate([[0], np.cumsum([len(x) for x in indices_list])]).astype(np.int64)
     seg_end = (np.concatenate([np.asarray(x, dtype=np.int64) for x in indices_list])
                if len(indices_list) else np.zeros(0, np.int64))
@@ -121,9 +125,9 @@ class AlignPlan:
         lp = np.ascontiguousarray(log_probs, dtype=np.float32)
         if lp.shape != (self.total_T, self.V):
             raise ValueError(f"log_probs must have shape {(self.total_T, self.V)}, got {lp.shape}")
-        if len(indices_list) != self.B:
-            raise ValueError(f"indices_list must hold one array per lattice ({self.B}), got {len(indices_list)}")
         seg_lat_off, seg_end = flat_segments(indices_list)
+        if seg_lat_off.shape[0] != self.B + 1:
+            raise ValueError(f"indices_list must hold one array per lattice ({self.B}), got {seg_lat_off.shape[0] - 1}")
         n_seg = int(seg_end.shape[0])
         rec = np.zeros(n_seg, SEGMENT_RECORD)
         final, status = np.empty(self.B, np.float32), np.empty(self.B, np.int32)

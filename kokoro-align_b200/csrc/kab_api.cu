@@ -19,6 +19,7 @@
 
 #include "kab_band.cuh"
 #include "kab_bandp.cuh"
+#include "kab_bandr.cuh"
 #include "kab_btpar.cuh"
 #include "kab_wide.cuh"
 #include "kab_common.cuh"
@@ -136,7 +137,9 @@ struct kab_plan {
   int sm_count = 0;
   int32_t stage_frames = 0, stage_bytes = 0;
   int32_t band_nw = 0;  // warps per CTA of the band kernel (ring of 104 * band_nw states)
-  int32_t band_nc = 0;  // > 0: the pipelined cluster kernel (kab_bandp.cuh) with clusters of band_nc CTAs
+  int32_t band_nc = 0;  // > 0: a cluster band kernel (kab_bandp.cuh / kab_bandq.cuh) with clusters of band_nc CTAs
+  bool band_q = false;  // the cluster kernel is kab_bandq_kernel / kab_bandr_kernel (two states per lane, KabBtLayoutQ)
+  bool band_r = false;  // ... kab_bandr_kernel (warp-specialised: prep warps, shared-memory mailboxes)
   kab_plan_info info{};
   std::vector<KabLattice> lists[N_QUEUES];
   bool any_bad_label = false;
@@ -357,11 +360,14 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
   int64_t bp_bytes = 0, scr_floats = 0, max_band_weff = 0;
   kab_plan_info &info = pl->info;
   info.n_lattices = B; info.device = device; info.total_frames = pl->total_T;
+  std::vector<int64_t> distinct_words(1024, 0);
+  const int n_mask = (V + 63) / 64;
   for (int64_t b = 0; b < B; ++b) {
     const int64_t T = t_off[b + 1] - t_off[b], L = l_off[b + 1] - l_off[b], S = 2 * L + 1;
     const int32_t *lab = labels + l_off[b];
     bool bad = false, special = false;
-    int64_t distinct_mask[1024] = {0};
+    int64_t *distinct_mask = distinct_words.data();  // (V <= 65535: 1024 words; only the first n_mask are in use)
+    std::fill(distinct_mask, distinct_mask + n_mask, (int64_t)0);
     int64_t distinct = 0;
     for (int64_t l = 0; l < L; ++l) {
       if (lab[l] < -V || lab[l] >= V) { bad = true; break; }
@@ -383,7 +389,7 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
       // compact numbering: blank 0, then the lattice's distinct label columns in ascending order
       int32_t *g = h_gather.data() + (size_t)b * pl->Vc;
       int32_t n = 1;
-      for (int w = 0; w < 1024; ++w)
+      for (int w = 0; w < n_mask; ++w)
         for (int64_t m = distinct_mask[w]; m; m &= m - 1) g[n++] = w * 64 + __builtin_ctzll((unsigned long long)m);
       for (int64_t l = 0; l < L; ++l)
         col16.push_back((uint16_t)(std::lower_bound(g + 1, g + n, lab[l]) - g));
@@ -445,12 +451,34 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
     const char *cl = getenv("KAB_BAND_CLUSTER");
     int want_nc = cl ? atoi(cl) : -1;
     const bool cluster_ok = nc <= 8 && kab_bandp_geom(pl->stage_bytes).smem_bytes <= 227 * 1024;
-    if (want_nc < 0 && cluster_ok) {
-      // resident clusters of this size: every SM holds one CTA of the cluster kernel
-      const int64_t resident = pl->sm_count / nc;
-      want_nc = (int64_t)pl->lists[Q_BAND].size() <= resident ? nc : 0;
-    }
-    if (cluster_ok && want_nc >= 1) {
+    // kab_bandq.cuh (two warps per scheduler, two states per lane: the shorter frame) when its ring
+    // of 40-slot warps fits a cluster of <= 8 CTAs and every lattice gets its own cluster at once;
+    // KAB_BAND_Q=0 keeps kab_bandp.cuh, =1 forces kab_bandq.cuh whenever its geometry allows
+    const int nwq = (int)((max_band_weff + 32 + KAB_BQ_OW - 1) / KAB_BQ_OW);
+    const int ncq = (nwq + KAB_BQ_CW - 1) / KAB_BQ_CW;
+    const bool q_ok = ncq <= 8 && kab_bandq_geom(pl->stage_bytes).smem_bytes <= 227 * 1024;
+    const char *qe = getenv("KAB_BAND_Q");
+    const int want_q = qe ? atoi(qe) : -1;
+    if (q_ok && want_q != 0 && (want_nc != 0) &&
+        (want_q >= 1 || (int64_t)pl->lists[Q_BAND].size() <= pl->sm_count / ncq)) {
+      pl->band_q = true;
+      const char *re = getenv("KAB_BAND_R");  // =0: kab_bandq.cuh (every warp does its own bookkeeping)
+      pl->band_r = (!re || atoi(re) != 0) && kab_bandr_geom(pl->stage_bytes).smem_bytes <= 227 * 1024;
+      pl->band_nc = ncq;
+      const int nwt = KAB_BQ_CW * ncq;
+      for (KabLattice &d : pl->lists[Q_BAND]) {
+        d.bp_off = bp_bytes;
+        bp_bytes += (int64_t)((d.T + 7) / 8) * 128 * nwt;  // [warp][group][32 lanes][4 B]
+        d.scr_off = pl->band_fifo_bytes / 4;
+        pl->band_fifo_bytes += (int64_t)align_up((int64_t)kab_bandq_ws_bytes(nwt), 256);
+      }
+    } else if ([&] {
+      if (want_nc < 0 && cluster_ok) {
+        // resident clusters of this size: every SM holds one CTA of the cluster kernel
+        const int64_t resident = pl->sm_count / nc;
+        want_nc = (int64_t)pl->lists[Q_BAND].size() <= resident ? nc : 0;
+      }
+      return cluster_ok && want_nc >= 1; }()) {
       pl->band_nc = std::min(8, std::max(nc, want_nc));
       const int nwt = KAB_BP_CW * pl->band_nc;
       for (KabLattice &d : pl->lists[Q_BAND]) {
@@ -491,7 +519,7 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
       steps += (double)d.T * (double)std::min<int64_t>(W, 2 * (int64_t)d.L + 1);
       tmax = std::max(tmax, (double)d.T);
     }
-    par_bt = sb ? atoi(sb) == 0 : steps * 0.55e-12 <= 0.6 * tmax * 40e-9;
+    par_bt = pl->band_q || (sb ? atoi(sb) == 0 : steps * 0.55e-12 <= 0.6 * tmax * 40e-9);  // (kab_bandq has no walker of its own)
   }
   if (par_bt) {
     for (const KabLattice &d : pl->lists[Q_BAND]) {
@@ -562,19 +590,22 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
     }
     if (!pl->lists[Q_BAND].empty() && pl->band_nc > 0) {
       if ((e = pool_malloc((void **)&pl->d_band_fifo, (size_t)pl->band_fifo_bytes)) != cudaSuccess) { rc = cuda_fail(e, "pool_malloc(band FIFOs)"); break; }
-      const KabBandpGeom geo = kab_bandp_geom(pl->stage_bytes);
-      if ((e = ensure_dyn_smem((const void *)kab_bandp_kernel, device, geo.smem_bytes)) != cudaSuccess) { rc = cuda_fail(e, "cudaFuncSetAttribute(bandp)"); break; }
-      pl->smem[Q_BAND] = geo.smem_bytes;
+      const size_t smem_b = pl->band_r ? kab_bandr_geom(pl->stage_bytes).smem_bytes
+                                       : (pl->band_q ? kab_bandq_geom(pl->stage_bytes).smem_bytes : kab_bandp_geom(pl->stage_bytes).smem_bytes);
+      const void *fn = pl->band_r ? (const void *)kab_bandr_kernel : (pl->band_q ? (const void *)kab_bandq_kernel : (const void *)kab_bandp_kernel);
+      const int threads = pl->band_r ? KAB_BR_THREADS : (pl->band_q ? KAB_BQ_THREADS : KAB_BP_THREADS);
+      if ((e = ensure_dyn_smem(fn, device, smem_b)) != cudaSuccess) { rc = cuda_fail(e, "cudaFuncSetAttribute(cluster band)"); break; }
+      pl->smem[Q_BAND] = smem_b;
       cudaLaunchConfig_t cfg{};
       cudaLaunchAttribute at[1];
       at[0].id = cudaLaunchAttributeClusterDimension;
       at[0].val.clusterDim.x = (unsigned)pl->band_nc; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
       cfg.gridDim = dim3((unsigned)(pl->band_nc * pl->sm_count), 1, 1);
-      cfg.blockDim = dim3(KAB_BP_THREADS, 1, 1);
-      cfg.dynamicSmemBytes = geo.smem_bytes;
+      cfg.blockDim = dim3((unsigned)threads, 1, 1);
+      cfg.dynamicSmemBytes = smem_b;
       cfg.attrs = at; cfg.numAttrs = 1;
       int ncl = 0;
-      if ((e = cudaOccupancyMaxActiveClusters(&ncl, kab_bandp_kernel, &cfg)) != cudaSuccess) { rc = cuda_fail(e, "cudaOccupancyMaxActiveClusters(bandp)"); break; }
+      if ((e = cudaOccupancyMaxActiveClusters(&ncl, fn, &cfg)) != cudaSuccess) { rc = cuda_fail(e, "cudaOccupancyMaxActiveClusters(cluster band)"); break; }
       ncl = (int)std::min<int64_t>(std::max(ncl, 1), (int64_t)pl->lists[Q_BAND].size());
       pl->grid[Q_BAND] = ncl * pl->band_nc;
     } else if (!pl->lists[Q_BAND].empty()) {
@@ -675,7 +706,7 @@ int kab_plan_run_device(kab_plan *pl, const float *d_log_probs, int32_t *d_best_
     pb.debug = dbg;
 #endif
     if (pl->band_nc > 0) {
-      KAB_CUDA(cudaMemsetAsync(pl->d_band_fifo, 0, (size_t)pl->band_fifo_bytes, stream));
+      if (!pl->band_r) KAB_CUDA(cudaMemsetAsync(pl->d_band_fifo, 0, (size_t)pl->band_fifo_bytes, stream));  // (bandr: mailboxes in shared memory)
       pb.fifo = pl->d_band_fifo;
 #ifdef KAB_BANDP_TIMING
       static long long *pdbg = nullptr;
@@ -704,20 +735,65 @@ int kab_plan_run_device(kab_plan *pl, const float *d_log_probs, int32_t *d_best_
       at[0].id = cudaLaunchAttributeClusterDimension;
       at[0].val.clusterDim.x = (unsigned)pl->band_nc; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
       cfg.gridDim = dim3((unsigned)pl->grid[Q_BAND], 1, 1);
-      cfg.blockDim = dim3(KAB_BP_THREADS, 1, 1);
+      cfg.blockDim = dim3((unsigned)(pl->band_r ? KAB_BR_THREADS : (pl->band_q ? KAB_BQ_THREADS : KAB_BP_THREADS)), 1, 1);
       cfg.dynamicSmemBytes = pl->smem[Q_BAND];
       cfg.stream = stream;
       cfg.attrs = at; cfg.numAttrs = 1;
       pb.end_state = pl->d_end_state;  // nullptr: the kernel walks back itself
-      KAB_CUDA(cudaLaunchKernelEx(&cfg, kab_bandp_kernel, (const KabLattice *)pl->d_lists[Q_BAND],
-                                  (int)pl->lists[Q_BAND].size(), pb));
+      const int n_band = (int)pl->lists[Q_BAND].size();
+      const dim3 mg((unsigned)pl->bt_blocks, (unsigned)((pl->bt_max_wl + KAB_BT_THREADS - 1) / KAB_BT_THREADS));
+      if (pl->band_q) {
+#ifdef KAB_BANDQ_TIMING
+        static long long *qdbg = nullptr;
+        if (!qdbg) cudaMalloc((void **)&qdbg, (64 * 28 + 8) * sizeof(long long));
+        cudaMemsetAsync(qdbg, 0, (64 * 28 + 8) * sizeof(long long), stream);
+        pb.debug = qdbg;
+        struct BandqDbgPrint {
+          long long *d; cudaStream_t s; int nw;
+          ~BandqDbgPrint() {
+            static long long h[64 * 28 + 8];
+            cudaStreamSynchronize(s);
+            cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+            long long ct[4] = {0, 0, 0, 0}, cn[4] = {0, 0, 0, 0}, cw[4] = {0, 0, 0, 0};
+            for (int w = 0; w < nw; ++w)
+              for (int k = 0; k < 4; ++k) {
+                const long long *c = h + 64 * 16 + 8 + w * 12;
+                ct[k] += c[k]; cn[k] += c[4 + k]; cw[k] += c[8 + k];
+              }
+            const char *names[4] = {"free / head (no message, edge body)", "no message, safe body", "message + edge body", "message + safe body"};
+            for (int k = 0; k < 4; ++k)
+              fprintf(stderr, "groups [%s]: %lld, %.0f cycles each, of which waiting %.0f\n", names[k], cn[k],
+                      cn[k] ? (double)ct[k] / cn[k] : 0.0, cn[k] ? (double)cw[k] / cn[k] : 0.0);
+            for (int w = 0; w < nw; w += 9) {
+              const long long *x = h + w * 16;
+              const double n = (double)(x[7] ? x[7] : 1);
+              fprintf(stderr, "warp %2d: per group: ghost %5.0f emis %4.0f comp %5.0f pub %4.0f bp %4.0f rel %4.0f | total %lld cyc = %.0f / group, %lld groups, need %lld, safe %lld, wait/need %.0f, comp safe %.0f slow %.0f\n",
+                      w, x[0] / n, x[1] / n, x[2] / n, x[3] / n, x[5] / n, x[4] / n, x[6], x[6] / n, x[7], x[9], x[10], x[9] ? (double)x[11] / x[9] : 0.0,
+                      x[10] ? (double)(x[2] - x[13]) / x[10] : 0.0, x[7] - x[10] ? (double)x[13] / (x[7] - x[10]) : 0.0);
+            }
+          }
+        } qdbg_print{qdbg, stream, KAB_BQ_CW * pl->band_nc};
+#endif
+        const int nwt = KAB_BQ_CW * pl->band_nc;
+        if (pl->band_r)
+          KAB_CUDA(cudaLaunchKernelEx(&cfg, kab_bandr_kernel, (const KabLattice *)pl->d_lists[Q_BAND], n_band, pb));
+        else
+          KAB_CUDA(cudaLaunchKernelEx(&cfg, kab_bandq_kernel, (const KabLattice *)pl->d_lists[Q_BAND], n_band, pb));
+        kab_bt_maps_kernel<KabBtLayoutQ><<<mg, KAB_BT_THREADS, 0, stream>>>(pl->d_lists[Q_BAND], pl->d_bt_meta, n_band, pl->d_bp,
+                                                                            d_status, pl->d_bt_maps, pl->W, nwt);
+        kab_bt_stitch_kernel<KabBtLayoutQ><<<n_band, 1024, 0, stream>>>(pl->d_lists[Q_BAND], pl->d_bt_meta, pb, pl->d_end_state,
+                                                                        pl->d_bt_maps, pl->d_bt_entry, nwt);
+      } else {
+        const int nwt = KAB_BP_CW * pl->band_nc;
+        KAB_CUDA(cudaLaunchKernelEx(&cfg, kab_bandp_kernel, (const KabLattice *)pl->d_lists[Q_BAND], n_band, pb));
+        if (pl->d_end_state) {
+          kab_bt_maps_kernel<KabBtLayoutP><<<mg, KAB_BT_THREADS, 0, stream>>>(pl->d_lists[Q_BAND], pl->d_bt_meta, n_band, pl->d_bp,
+                                                                              d_status, pl->d_bt_maps, pl->W, nwt);
+          kab_bt_stitch_kernel<KabBtLayoutP><<<n_band, 1024, 0, stream>>>(pl->d_lists[Q_BAND], pl->d_bt_meta, pb, pl->d_end_state,
+                                                                          pl->d_bt_maps, pl->d_bt_entry, nwt);
+        }
+      }
       if (pl->d_end_state) {
-        const int n_band = (int)pl->lists[Q_BAND].size(), nwt = KAB_BP_CW * pl->band_nc;
-        const dim3 mg((unsigned)pl->bt_blocks, (unsigned)((pl->bt_max_wl + KAB_BT_THREADS - 1) / KAB_BT_THREADS));
-        kab_bt_maps_kernel<<<mg, KAB_BT_THREADS, 0, stream>>>(pl->d_lists[Q_BAND], pl->d_bt_meta, n_band, pl->d_bp,
-                                                              d_status, pl->d_bt_maps, pl->W, nwt);
-        kab_bt_stitch_kernel<<<n_band, 1024, 0, stream>>>(pl->d_lists[Q_BAND], pl->d_bt_meta, pb, pl->d_end_state,
-                                                          pl->d_bt_maps, pl->d_bt_entry, nwt);
         const dim3 gg((unsigned)n_band, (unsigned)((pl->max_T[Q_BAND] + KAB_BT_GATHER_FRAMES - 1) / KAB_BT_GATHER_FRAMES));
         kab_bt_gather_kernel<<<gg, 256, 0, stream>>>(pl->d_lists[Q_BAND], pb);
       }

@@ -18,12 +18,34 @@
 //      blocks at once (best_path);
 //   3. kab_bt_gather_kernel: best_labels and best_scores of the path (align.py:105-107), coalesced
 //      over the frames.
-// Backpointer layout (written by kab_bandp_kernel): byte of (frame t, state v) at
+// Backpointer layouts (template parameter of the kernels):
+//   KabBtLayoutP (kab_bandp_kernel): byte of (frame t, state v) at
 //     bp[((reg * n_groups + t / 8) * 32 + col) * 8 + t % 8],   slot = v mod R, reg = slot / 104,
-//     col = (slot % 104) / 4, move = (byte >> 2 * (slot & 3)) & 3.
+//     col = (slot % 104) / 4, move = (byte >> 2 * (slot & 3)) & 3;
+//   KabBtLayoutQ (kab_bandq_kernel): 32-bit word of (group t / 8, lane) at
+//     bp[((reg * n_groups + t / 8) * 32 + 12 + (slot % 40) / 2) * 4],   reg = slot / 40,
+//     move = (word >> (4 * (t % 8) + 2 * (slot & 1))) & 3.
 #pragma once
 #include "kab_band.cuh"
+#include "kab_bandq.cuh"
 #include "kab_common.cuh"
+
+struct KabBtLayoutP {
+  static constexpr int OW = KAB_BAND_OW;  // ring slots per warp region
+  static constexpr int GROW = 256;        // bytes per region and 8-frame group
+  static __device__ __forceinline__ int move(const unsigned char *gp, int rs, int f) {
+    const unsigned int byte = gp[((rs >> 2) << 3) + f];
+    return (int)((byte >> (2 * (rs & 3))) & 3u);
+  }
+};
+struct KabBtLayoutQ {
+  static constexpr int OW = KAB_BQ_OW;
+  static constexpr int GROW = 128;
+  static __device__ __forceinline__ int move(const unsigned char *gp, int rs, int f) {
+    const uint32_t word = *reinterpret_cast<const uint32_t *>(gp + (KAB_BQ_GH + (rs >> 1)) * 4);
+    return (int)((word >> (4 * f + 2 * (rs & 1))) & 3u);
+  }
+};
 
 #define KAB_BT_BLOCK 1024   // frames per block
 #define KAB_BT_THREADS 128  // threads per CTA of the map kernel (= entry states per CTA)
@@ -38,15 +60,16 @@ struct KabBtMeta {       // one per lattice of the band list (same order)
 
 // walker: state v, its position rs inside ring region reg, and gp = the backpointer rows of that
 // region for the CURRENT 8-frame group (the caller moves it down by 256 bytes per group)
+template <class LY>
 struct KabBtWalker {
   int v, rs, reg;
   const unsigned char *gp;
   __device__ __forceinline__ void init(int v0, int R, const unsigned char *bp, int64_t stride, int g) {
     v = v0;
     const int slot = v0 % R;
-    reg = slot / KAB_BAND_OW;
-    rs = slot - reg * KAB_BAND_OW;
-    gp = bp + reg * stride + (size_t)g * 256;
+    reg = slot / LY::OW;
+    rs = slot - reg * LY::OW;
+    gp = bp + reg * stride + (size_t)g * LY::GROW;
   }
   // one frame back (frame f of the current group); returns the state AT that frame (before the move).
   // The region change (once per ~370 frames of a walker) is a real branch into a non-inlined helper:
@@ -60,13 +83,12 @@ struct KabBtWalker {
     return w;
   }
   __device__ __forceinline__ int step(int f, int NWT, int64_t stride) {
-    const unsigned int byte = gp[((rs >> 2) << 3) + f];
     const int at = v;
-    const int mv = (int)((byte >> (2 * (rs & 3))) & 3u);
+    const int mv = LY::move(gp, rs, f);
     v -= mv;  // (a walker that started in an inactive state may run below 0: its value is never used,
     rs -= mv;  //  and the addresses come from rs / reg, which stay inside the workspace)
     if (rs < 0) {  // into the region below (a move crosses at most one boundary)
-      rs += KAB_BAND_OW;
+      rs += LY::OW;
       const Wrap w = wrap_region(reg, NWT, stride);
       reg = w.reg;
       gp += w.delta;
@@ -80,9 +102,9 @@ struct KabBtWalker {
     if ((te & 7) != 7) {  // partial group at the top (the last frames of the lattice)
       for (int k = te & 7; k >= 0; --k) f(g * 8 + k, step(k, NWT, stride));
       --g;
-      gp -= 256;
+      gp -= LY::GROW;
     }
-    for (; g >= (t0 >> 3); --g, gp -= 256) {
+    for (; g >= (t0 >> 3); --g, gp -= LY::GROW) {
 #pragma unroll
       for (int k = 7; k >= 0; --k) f(g * 8 + k, step(k, NWT, stride));
     }
@@ -95,6 +117,7 @@ __device__ __forceinline__ int kab_bt_lo(int64_t S, int64_t t, int64_t T, int W)
 }
 
 // grid.x = total blocks of all lattices, grid.y = chunks of KAB_BT_THREADS entry states
+template <class LY>
 __global__ void __launch_bounds__(KAB_BT_THREADS)
 kab_bt_maps_kernel(const KabLattice *__restrict__ lats, const KabBtMeta *__restrict__ meta, int n_lat,
                    const unsigned char *__restrict__ bpw, const int32_t *__restrict__ status, int32_t *__restrict__ maps,
@@ -105,20 +128,21 @@ kab_bt_maps_kernel(const KabLattice *__restrict__ lats, const KabBtMeta *__restr
   const KabBtMeta m = meta[li];
   if (status[lat.index] != 0) return;
   const int b = (int)blockIdx.x - m.first_block;
-  const int T = lat.T, S = 2 * lat.L + 1, R = KAB_BAND_OW * NWT, n_groups = (T + 7) / 8;
+  const int T = lat.T, S = 2 * lat.L + 1, R = LY::OW * NWT, n_groups = (T + 7) / 8;
   const int t0 = b * KAB_BT_BLOCK, te = min(T, t0 + KAB_BT_BLOCK) - 1;
   const int lo = kab_bt_lo(S, te, T, W), hi = min(lo + W, S);
   const int j = blockIdx.y * KAB_BT_THREADS + threadIdx.x;
   if (lo + j >= hi) return;
   const unsigned char *bp = bpw + lat.bp_off;
-  const int64_t stride = (int64_t)n_groups * 256;
-  KabBtWalker w;
+  const int64_t stride = (int64_t)n_groups * LY::GROW;
+  KabBtWalker<LY> w;
   w.init(lo + j, R, bp, stride, te >> 3);
   w.walk(te, t0, NWT, stride, [](int, int) {});
   maps[m.map_off + (int64_t)b * m.wl + j] = w.v;
 }
 
 // one CTA per lattice
+template <class LY>
 __global__ void __launch_bounds__(1024)
 kab_bt_stitch_kernel(const KabLattice *__restrict__ lats, const KabBtMeta *__restrict__ meta, KabParams p,
                      const int32_t *__restrict__ end_state, const int32_t *__restrict__ maps,
@@ -126,7 +150,7 @@ kab_bt_stitch_kernel(const KabLattice *__restrict__ lats, const KabBtMeta *__res
   const KabLattice lat = lats[blockIdx.x];
   const KabBtMeta m = meta[blockIdx.x];
   if (p.status[lat.index] != 0) return;
-  const int T = lat.T, S = 2 * lat.L + 1, W = p.W, R = KAB_BAND_OW * NWT, n_groups = (T + 7) / 8;
+  const int T = lat.T, S = 2 * lat.L + 1, W = p.W, R = LY::OW * NWT, n_groups = (T + 7) / 8;
   int32_t *ent = entry + m.first_block;
   // window start of every block's last frame (64-bit divisions): all threads, off the chain below
   for (int b = threadIdx.x; b < m.n_blocks; b += blockDim.x)
@@ -144,11 +168,11 @@ kab_bt_stitch_kernel(const KabLattice *__restrict__ lats, const KabBtMeta *__res
   // every block re-walked from its entry state, one thread each: only the backpointer bytes are on
   // the dependent chain (eight frames share a sector)
   const unsigned char *bp = p.bp + lat.bp_off;
-  const int64_t stride = (int64_t)n_groups * 256;
+  const int64_t stride = (int64_t)n_groups * LY::GROW;
   int32_t *out_path = p.best_path + lat.t_off;
   for (int b = threadIdx.x; b < m.n_blocks; b += blockDim.x) {
     const int t0 = b * KAB_BT_BLOCK, te = min(T, t0 + KAB_BT_BLOCK) - 1;
-    KabBtWalker w;
+    KabBtWalker<LY> w;
     w.init(ent[b], R, bp, stride, te >> 3);
     w.walk(te, t0, NWT, stride, [&](int t, int at) { out_path[t] = at; });
   }

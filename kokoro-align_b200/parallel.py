@@ -113,11 +113,14 @@ def sum_over_ranks(x, group=None, device=None):
     return float(t.item())
 
 
-def bind_host_to_gpu(device):
+def bind_host_to_gpu(device, world=1):
     """Pin this process to the CPU cores NVML reports as local to GPU `device` (same NUMA node /
     PCIe root), BEFORE its pinned staging buffers are allocated: first-touch then places them in
     the memory next to the GPU, so the H2D streams of the ranks of one box do not all cross the
-    same socket link.  Returns the cpu set, or None when NVML / affinity is unavailable."""
+    same socket link.  When NVML gives every GPU the same mask (one NUMA node, or a container
+    that hides the topology) the `world` ranks would all sit on the same cores: the mask is then
+    cut into `world` contiguous slices and rank `device` takes its own.  Returns the cpu set, or
+    None when NVML / affinity is unavailable."""
     import os
     try:
         import pynvml
@@ -146,6 +149,24 @@ def bind_host_to_gpu(device):
         cpus &= set(os.sched_getaffinity(0))
         if not cpus:
             return None
+        if world > 1 and len(cpus) >= 2 * world:
+            # do the other GPUs report the same mask?  then share it out instead of piling up
+            same = True
+            try:
+                pynvml.nvmlInit()
+                try:
+                    for k in range(min(world, pynvml.nvmlDeviceGetCount())):
+                        wk = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(k), n_words)
+                        if list(wk) != list(words):
+                            same = False
+                finally:
+                    pynvml.nvmlShutdown()
+            except Exception:  # noqa: BLE001
+                same = False
+            if same:
+                order = sorted(cpus)
+                per = len(order) // world
+                cpus = set(order[(device % world) * per:(device % world + 1) * per])
         os.sched_setaffinity(0, cpus)
         return cpus
     except Exception:  # noqa: BLE001  (no NVML, no permission, non-Linux: run unbound)

@@ -205,16 +205,20 @@ def test_random_shapes_and_beams(kab, seed):
     _compare_batch(kab, lp, t_off, labels, l_off, beam_size=W)
 
 
-@pytest.mark.parametrize("beam_size,cluster,serial_bt", [(1000, 1, 0), (64, 1, 0), (200, 2, 0), (1000, 1, 1), (200, 2, 1),
-                                                         (1000, 0, 0), (64, 0, 0), (300, 0, 0)])
-def test_both_band_kernels(kab, monkeypatch, beam_size, cluster, serial_bt):
-    """The two band kernels against the C oracle, forced through KAB_BAND_CLUSTER: the pipelined
-    cluster kernel (kab_bandp.cuh, the default when every lattice gets its own cluster) and the
-    single-CTA kernel (kab_band.cuh, the default for larger batches, = 0 here).  The cluster
-    kernel with both tracebacks: the parallel block-map composition (kab_btpar.cuh, default) and
-    its own single-thread walker (KAB_BAND_SERIAL_BT=1)."""
+@pytest.mark.parametrize("beam_size,cluster,serial_bt,q", [
+    (1000, 1, 0, 1), (64, 1, 0, 1), (200, 1, 0, 1), (2400, 1, 0, 1), (1, 1, 0, 1),
+    (1000, 1, 0, 0), (64, 1, 0, 0), (200, 2, 0, 0), (1000, 1, 1, 0), (200, 2, 1, 0),
+    (1000, 0, 0, 0), (64, 0, 0, 0), (300, 0, 0, 0)])
+def test_both_band_kernels(kab, monkeypatch, beam_size, cluster, serial_bt, q):
+    """The three band kernels against the C oracle, forced through KAB_BAND_CLUSTER / KAB_BAND_Q:
+    kab_bandq.cuh (two warps per scheduler, two states per lane; the default when every lattice
+    gets its own cluster; always the parallel traceback), kab_bandp.cuh (one warp per scheduler, four
+    states per lane; KAB_BAND_Q=0) with both tracebacks -- the parallel block-map composition
+    (kab_btpar.cuh) and its own single-thread walker (KAB_BAND_SERIAL_BT=1) -- and the single-CTA
+    kernel (kab_band.cuh, the default for larger batches, KAB_BAND_CLUSTER=0)."""
     from kokoro_align_b200 import synth
     monkeypatch.setenv("KAB_BAND_CLUSTER", str(cluster))
+    monkeypatch.setenv("KAB_BAND_Q", str(q))
     monkeypatch.setenv("KAB_BAND_SERIAL_BT", str(serial_bt))   # 0 forces the parallel traceback
     T = np.array([12000, 7001, 3000, 41, 5003])
     L = np.round(0.14 * T).astype(np.int64)
@@ -222,6 +226,26 @@ def test_both_band_kernels(kab, monkeypatch, beam_size, cluster, serial_bt):
     lp, t_off, labels, l_off = synth.make_batch(T, L, seed=4300 + beam_size, planted=True)
     info = _compare_batch(kab, lp, t_off, labels, l_off, beam_size=beam_size)
     assert info.n_class[1] >= 4
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13, 14])
+def test_bandq_random_shapes(kab, monkeypatch, seed):
+    """kab_bandq.cuh forced on randomised (T, L, beam_size) batches: every cluster size 1..8, ring
+    wrap-arounds (long T with narrow beams), S/T up to 3, tie stress, tiny lattices."""
+    from kokoro_align_b200 import synth
+    monkeypatch.setenv("KAB_BAND_Q", "1")
+    rng = np.random.default_rng(seed)
+    W = int(rng.choice([8, 9, 40, 41, 288, 289, 1000, 1248, 1249, 2528])) if seed % 2 else int(rng.integers(1, 2529))
+    n = 24
+    T = rng.integers(1, 4000, n)
+    ratio = rng.choice([0.02, 0.14, 0.5, 1.0, 1.45], n)
+    L = np.minimum(np.maximum(0, np.round(ratio * T)).astype(np.int64), (3 * T - 1) // 2)
+    L[:3] = [200, 0, 1]
+    T[:3] = [9000, 1, 2]
+    lp, t_off, labels, l_off = synth.make_batch(T, L, seed=7700 + 100 * seed, planted=bool(seed % 2))
+    if seed % 3 == 0:
+        lp = (np.round(lp * 2) / 2).astype(np.float32)
+    _compare_batch(kab, lp, t_off, labels, l_off, beam_size=W)
 
 
 @pytest.mark.parametrize("V", [128, 256, 512, 600, 4096])
