@@ -140,6 +140,7 @@ struct kab_plan {
   int32_t band_nc = 0;  // > 0: a cluster band kernel (kab_bandp.cuh / kab_bandq.cuh) with clusters of band_nc CTAs
   bool band_q = false;  // the cluster kernel is kab_bandq_kernel / kab_bandr_kernel (two states per lane, KabBtLayoutQ)
   bool band_r = false;  // ... kab_bandr_kernel (warp-specialised: prep warps, shared-memory mailboxes)
+  int32_t band_cw = 0;  // compute warps per CTA of that kernel (ring of 40 * band_cw * band_nc slots)
   kab_plan_info info{};
   std::vector<KabLattice> lists[N_QUEUES];
   bool any_bad_label = false;
@@ -457,15 +458,25 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
     const int nwq = (int)((max_band_weff + 32 + KAB_BQ_OW - 1) / KAB_BQ_OW);
     const int ncq = (nwq + KAB_BQ_CW - 1) / KAB_BQ_CW;
     const bool q_ok = ncq <= 8 && kab_bandq_geom(pl->stage_bytes).smem_bytes <= 227 * 1024;
+    // kab_bandr.cuh: the same lanes with ONE compute warp per scheduler and the bookkeeping on helper
+    // warps -- by far the shortest frame, at 4 compute warps per CTA (7 CTAs for the 1000-wide band).
+    // Its clusters take lattices from the work queue, so a plan may hold more lattices than clusters.
+    // KAB_BAND_R=0 disables it, =1 forces it whenever its geometry allows.
+    const int ncr = (nwq + KAB_BR_CW - 1) / KAB_BR_CW;
+    const bool r_ok = ncr <= 8 && pl->stage_frames == KAB_BR_F && kab_bandr_geom(pl->stage_bytes).smem_bytes <= 227 * 1024;
     const char *qe = getenv("KAB_BAND_Q");
     const int want_q = qe ? atoi(qe) : -1;
-    if (q_ok && want_q != 0 && (want_nc != 0) &&
-        (want_q >= 1 || (int64_t)pl->lists[Q_BAND].size() <= pl->sm_count / ncq)) {
+    const char *re = getenv("KAB_BAND_R");
+    const int want_r = re ? atoi(re) : -1;
+    const int64_t n_band = (int64_t)pl->lists[Q_BAND].size();
+    const bool use_r = r_ok && want_r != 0 && want_nc != 0 && want_q != 0 && (want_r >= 1 || n_band <= 49);
+    const bool use_q = !use_r && q_ok && want_q != 0 && want_nc != 0 && (want_q >= 1 || n_band <= pl->sm_count / ncq);
+    if (use_r || use_q) {
       pl->band_q = true;
-      const char *re = getenv("KAB_BAND_R");  // =0: kab_bandq.cuh (every warp does its own bookkeeping)
-      pl->band_r = (!re || atoi(re) != 0) && kab_bandr_geom(pl->stage_bytes).smem_bytes <= 227 * 1024;
-      pl->band_nc = ncq;
-      const int nwt = KAB_BQ_CW * ncq;
+      pl->band_r = use_r;
+      pl->band_cw = use_r ? KAB_BR_CW : KAB_BQ_CW;
+      pl->band_nc = use_r ? ncr : ncq;
+      const int nwt = pl->band_cw * pl->band_nc;
       for (KabLattice &d : pl->lists[Q_BAND]) {
         d.bp_off = bp_bytes;
         bp_bytes += (int64_t)((d.T + 7) / 8) * 128 * nwt;  // [warp][group][32 lanes][4 B]
@@ -634,6 +645,7 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
   info.kernel_launches = 0;
   for (int q = 0; q < N_QUEUES; ++q) info.kernel_launches += pl->lists[q].empty() ? 0 : 1;
   if (!pl->bt_meta.empty()) info.kernel_launches += 3;  // kab_bt_maps_kernel, kab_bt_stitch_kernel, kab_bt_gather_kernel
+  if (pl->band_r) info.kernel_launches += 1;            // kab_finite_rows_kernel
   if (pl->Vc)                                          // kab_compact_kernel, kab_expand_labels_kernel
     for (int q : {Q_WARP, Q_BAND, Q_WIDE}) info.kernel_launches += pl->lists[q].empty() ? 0 : 2;
   *out = pl;
@@ -772,12 +784,70 @@ int kab_plan_run_device(kab_plan *pl, const float *d_log_probs, int32_t *d_best_
                       x[10] ? (double)(x[2] - x[13]) / x[10] : 0.0, x[7] - x[10] ? (double)x[13] / (x[7] - x[10]) : 0.0);
             }
           }
-        } qdbg_print{qdbg, stream, KAB_BQ_CW * pl->band_nc};
+        } qdbg_print{qdbg, stream, pl->band_cw * pl->band_nc};
 #endif
-        const int nwt = KAB_BQ_CW * pl->band_nc;
-        if (pl->band_r)
+        const int nwt = pl->band_cw * pl->band_nc;
+#ifdef KAB_BR_TRACE2
+        static long long *tdbg = nullptr;
+        if (!tdbg) cudaMalloc((void **)&tdbg, 64 * 256 * 4 * sizeof(long long));
+        cudaMemsetAsync(tdbg, 0, 64 * 256 * 4 * sizeof(long long), stream);
+        pb.debug = tdbg;
+        struct Trace2Dump {
+          long long *d; cudaStream_t s;
+          ~Trace2Dump() {
+            if (const char *tf = getenv("KAB_TRACE_FILE")) {
+              std::vector<long long> tr((size_t)64 * 256 * 4);
+              cudaStreamSynchronize(s);
+              cudaMemcpy(tr.data(), d, tr.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+              if (FILE *f = fopen(tf, "wb")) { fwrite(tr.data(), sizeof(long long), tr.size(), f); fclose(f); }
+            }
+          }
+        } trace2_dump{tdbg, stream};
+#endif
+#ifdef KAB_BANDR_TIMING
+        static long long *rdbg = nullptr;
+        const size_t rdbg_n = 64 * 26 + (size_t)64 * 16384 * 2;
+        if (!rdbg) cudaMalloc((void **)&rdbg, rdbg_n * sizeof(long long));
+        cudaMemsetAsync(rdbg, 0, rdbg_n * sizeof(long long), stream);
+        pb.debug = rdbg;
+        struct BandrDbgPrint {
+          long long *d; cudaStream_t s; int nw;
+          ~BandrDbgPrint() {
+            static long long h[64 * 26];
+            cudaStreamSynchronize(s);
+            cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+            if (const char *tf = getenv("KAB_TRACE_FILE")) {  // per-group start times of every compute warp
+              std::vector<long long> tr((size_t)64 * 16384 * 2);
+              cudaMemcpy(tr.data(), d + 64 * 26, tr.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+              if (FILE *f = fopen(tf, "wb")) { fwrite(tr.data(), sizeof(long long), tr.size(), f); fclose(f); }
+            }
+            long long a[16] = {0};
+            for (int w = 0; w < nw; ++w)
+              for (int k = 0; k < 15; ++k) a[k] += h[w * 16 + k];
+            const double n = (double)(a[6] ? a[6] : 1);
+            fprintf(stderr, "compute warps, per group: tile %.0f msg %.0f (waiting %.0f) frames %.0f pub %.0f bp %.0f | total %.0f cycles / group\n",
+                    a[0] / n, a[1] / n, a[8] / n, a[2] / n, a[3] / n, a[4] / n, a[5] / n);
+            fprintf(stderr, "  groups without a message: %lld, %.0f cycles each (waiting %.0f); with: %lld, %.0f cycles each (waiting %.0f)\n",
+                    a[10], a[10] ? (double)a[9] / a[10] : 0.0, a[10] ? (double)a[11] / a[10] : 0.0,
+                    a[13], a[13] ? (double)a[12] / a[13] : 0.0, a[13] ? (double)a[14] / a[13] : 0.0);
+            long long ft = 0, fn = 0;
+            for (int w = 0; w < nw; ++w) { ft += h[64 * 24 + w * 2]; fn += h[64 * 24 + w * 2 + 1]; }
+            fprintf(stderr, "  fast-path groups: %lld of %lld, %.0f cycles each; the others %.0f cycles each\n", fn, a[6], fn ? (double)ft / fn : 0.0,
+                    a[6] - fn ? (double)(a[5] - ft) / (a[6] - fn) : 0.0);
+            long long b[8] = {0};
+            for (int w = 0; w < nw; ++w)
+              for (int k = 0; k < 6; ++k) b[k] += h[64 * 16 + w * 8 + k];
+            const double m = (double)(b[5] ? b[5] : 1);
+            fprintf(stderr, "prep warps, per group: waiting for the slot %.0f, tile %.0f, stage / backpointers %.0f | total %.0f, safe groups %.0f %%\n",
+                    b[0] / m, b[1] / m, b[2] / m, b[3] / m, 100.0 * b[4] / m);
+          }
+        } rdbg_print{rdbg, stream, nwt};
+#endif
+        if (pl->band_r) {
           KAB_CUDA(cudaLaunchKernelEx(&cfg, kab_bandr_kernel, (const KabLattice *)pl->d_lists[Q_BAND], n_band, pb));
-        else
+          const dim3 fg((unsigned)n_band, (unsigned)((pl->max_T[Q_BAND] + KAB_FIN_ROWS - 1) / KAB_FIN_ROWS));
+          kab_finite_rows_kernel<<<fg, 256, 0, stream>>>(pl->d_lists[Q_BAND], pf.lp, pf.V, d_status, d_final_score);
+        } else
           KAB_CUDA(cudaLaunchKernelEx(&cfg, kab_bandq_kernel, (const KabLattice *)pl->d_lists[Q_BAND], n_band, pb));
         kab_bt_maps_kernel<KabBtLayoutQ><<<mg, KAB_BT_THREADS, 0, stream>>>(pl->d_lists[Q_BAND], pl->d_bt_meta, n_band, pl->d_bp,
                                                                             d_status, pl->d_bt_maps, pl->W, nwt);
