@@ -205,20 +205,23 @@ def test_random_shapes_and_beams(kab, seed):
     _compare_batch(kab, lp, t_off, labels, l_off, beam_size=W)
 
 
-@pytest.mark.parametrize("beam_size,cluster,serial_bt,q", [
-    (1000, 1, 0, 1), (64, 1, 0, 1), (200, 1, 0, 1), (2400, 1, 0, 1), (1, 1, 0, 1),
-    (1000, 1, 0, 0), (64, 1, 0, 0), (200, 2, 0, 0), (1000, 1, 1, 0), (200, 2, 1, 0),
-    (1000, 0, 0, 0), (64, 0, 0, 0), (300, 0, 0, 0)])
-def test_both_band_kernels(kab, monkeypatch, beam_size, cluster, serial_bt, q):
-    """The three band kernels against the C oracle, forced through KAB_BAND_CLUSTER / KAB_BAND_Q:
-    kab_bandq.cuh (two warps per scheduler, two states per lane; the default when every lattice
-    gets its own cluster; always the parallel traceback), kab_bandp.cuh (one warp per scheduler, four
-    states per lane; KAB_BAND_Q=0) with both tracebacks -- the parallel block-map composition
-    (kab_btpar.cuh) and its own single-thread walker (KAB_BAND_SERIAL_BT=1) -- and the single-CTA
-    kernel (kab_band.cuh, the default for larger batches, KAB_BAND_CLUSTER=0)."""
+@pytest.mark.parametrize("beam_size,cluster,serial_bt,q,r", [
+    (1000, 1, 0, 1, 1), (64, 1, 0, 1, 1), (200, 1, 0, 1, 1), (1200, 1, 0, 1, 1), (1, 1, 0, 1, 1),
+    (1000, 1, 0, 1, 0), (64, 1, 0, 1, 0), (200, 1, 0, 1, 0), (2400, 1, 0, 1, 0), (1, 1, 0, 1, 0),
+    (1000, 1, 0, 0, 0), (64, 1, 0, 0, 0), (200, 2, 0, 0, 0), (1000, 1, 1, 0, 0), (200, 2, 1, 0, 0),
+    (1000, 0, 0, 0, 0), (64, 0, 0, 0, 0), (300, 0, 0, 0, 0)])
+def test_both_band_kernels(kab, monkeypatch, beam_size, cluster, serial_bt, q, r):
+    """The four band kernels against the C oracle, forced through KAB_BAND_CLUSTER / KAB_BAND_Q /
+    KAB_BAND_R: kab_bandr.cuh (warp-specialised: one compute warp per scheduler, prep warps, mailboxes
+    in shared memory; the default for up to 49 lattices; always the parallel traceback), kab_bandq.cuh
+    (the same lanes, every warp does its own bookkeeping; KAB_BAND_R=0), kab_bandp.cuh (four states per
+    lane; KAB_BAND_Q=0) with both tracebacks -- the parallel block-map composition (kab_btpar.cuh) and
+    its own single-thread walker (KAB_BAND_SERIAL_BT=1) -- and the single-CTA kernel (kab_band.cuh,
+    the default for larger batches, KAB_BAND_CLUSTER=0)."""
     from kokoro_align_b200 import synth
     monkeypatch.setenv("KAB_BAND_CLUSTER", str(cluster))
     monkeypatch.setenv("KAB_BAND_Q", str(q))
+    monkeypatch.setenv("KAB_BAND_R", str(r))
     monkeypatch.setenv("KAB_BAND_SERIAL_BT", str(serial_bt))   # 0 forces the parallel traceback
     T = np.array([12000, 7001, 3000, 41, 5003])
     L = np.round(0.14 * T).astype(np.int64)
@@ -228,14 +231,17 @@ def test_both_band_kernels(kab, monkeypatch, beam_size, cluster, serial_bt, q):
     assert info.n_class[1] >= 4
 
 
-@pytest.mark.parametrize("seed", [11, 12, 13, 14])
-def test_bandq_random_shapes(kab, monkeypatch, seed):
-    """kab_bandq.cuh forced on randomised (T, L, beam_size) batches: every cluster size 1..8, ring
-    wrap-arounds (long T with narrow beams), S/T up to 3, tie stress, tiny lattices."""
+@pytest.mark.parametrize("seed,r", [(11, 0), (12, 0), (13, 0), (14, 0), (11, 1), (12, 1), (13, 1), (14, 1), (15, 1), (16, 1)])
+def test_bandq_random_shapes(kab, monkeypatch, seed, r):
+    """kab_bandq.cuh (r = 0) and kab_bandr.cuh (r = 1) forced on randomised (T, L, beam_size) batches:
+    every cluster size 1..8, ring wrap-arounds (long T with narrow beams), S/T up to 3, tie stress,
+    tiny lattices, more lattices than clusters (work queue)."""
     from kokoro_align_b200 import synth
     monkeypatch.setenv("KAB_BAND_Q", "1")
+    monkeypatch.setenv("KAB_BAND_R", str(r))
     rng = np.random.default_rng(seed)
-    W = int(rng.choice([8, 9, 40, 41, 288, 289, 1000, 1248, 1249, 2528])) if seed % 2 else int(rng.integers(1, 2529))
+    wmax = 1248 if r else 2528          # widest band of the kernel: 40 * CW * 8 - 32 ring slots
+    W = int(rng.choice([8, 9, 40, 41, 128, 129, 288, 289, 1000, wmax - 1, wmax])) if seed % 2 else int(rng.integers(1, wmax + 1))
     n = 24
     T = rng.integers(1, 4000, n)
     ratio = rng.choice([0.02, 0.14, 0.5, 1.0, 1.45], n)
