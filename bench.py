@@ -48,13 +48,11 @@ UNIT = "cells/s"
 REF_DIR = os.path.join(ROOT, "baseline", "_ref")
 
 
-def band_kernel_name(n_band, beam_size=1000):
-    """Which band kernel kab_plan_create picks (kab_api.cu): the cluster kernel when every band
-    lattice of the plan gets its own cluster at once."""
-    forced = os.environ.get("KAB_BAND_CLUSTER")
-    if forced is not None:
-        return "kab_bandp_kernel" if int(forced) >= 1 else "kab_band_kernel"
-    return "kab_bandp_kernel" if n_band <= 49 else "kab_band_kernel"
+def band_kernel_name(info):
+    """The kernel kab_plan_create chose for the band lattices (kab_plan_info.band_kernel)."""
+    from kokoro_align_b200 import _lib
+    name = _lib.BAND_KERNELS.get(int(info.band_kernel))
+    return f"{name} (cluster of {int(info.band_cluster)})" if name and info.band_cluster > 1 else name
 
 
 def load_peaks():
@@ -310,7 +308,7 @@ def sub_record(name, seed, steps, dev, peak, files_dir=None):
             "device_ms": ms, "cells_eval": int(info.cells_eval), "cells_nominal": int(info.cells_nominal),
             "cells_per_s": info.cells_eval / (ms * 1e-3), "ns_per_frame_longest": ms * 1e6 / int(T.max()),
             "e2e_ms": e2e_ms, "e2e_cells_per_s": info.cells_eval / (e2e_ms * 1e-3),
-            "kernel": band_kernel_name(int(info.n_class[1])), "gpu_launches_per_step": int(info.kernel_launches),
+            "kernel": band_kernel_name(info), "gpu_launches_per_step": int(info.kernel_launches),
             "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": alg / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": alg,
                          "note": "ONE sequential recurrence per lattice: latency bound (DESIGN.md section 4)"}})
@@ -599,7 +597,7 @@ def main():
             "gpu_launches": int(info.kernel_launches) * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "kab_warp_kernel" if info.n_class[0] >= info.n_class[1] else band_kernel_name(int(info.n_class[1])),
+                         "kernel": "kab_warp_kernel" if info.n_class[0] >= info.n_class[1] else band_kernel_name(info),
                          "algorithmic_bytes_per_launch": int(info.algorithmic_bytes), "kernel_ms": kernel_ms},
             "cpu_baseline": cpu, "clocks": clocks,
         }

@@ -66,7 +66,14 @@ typedef struct kab_plan_info {
   int64_t algorithmic_bytes;/* 4*min(V,D+1)*T + cells*b/8 + T*b/8 + 12*T, summed */
   int32_t kernel_launches;  /* kernels launched by one kab_plan_run_* */
   int32_t device;
+  int32_t band_kernel;      /* which kernel takes the KAB_CLASS_BAND lattices: KAB_BAND_KERNEL_* (0: none) */
+  int32_t band_cluster;     /* CTAs per cluster of that kernel (1 for the single-CTA kernel) */
 } kab_plan_info;
+
+#define KAB_BAND_KERNEL_CTA 1      /* kab_band_kernel: one CTA per lattice, two lattices per SM */
+#define KAB_BAND_KERNEL_CLUSTER 2  /* kab_bandp_kernel: cluster, four states per lane */
+#define KAB_BAND_KERNEL_CLUSTER2 3 /* kab_bandq_kernel: cluster, two states per lane */
+#define KAB_BAND_KERNEL_SPEC 4     /* kab_bandr_kernel: cluster, warp-specialised (prep warps, shared-memory mailboxes) */
 
 int kab_version(void);
 const char *kab_error_string(int code);

@@ -30,7 +30,10 @@ class PlanInfo(ctypes.Structure):
                 ("total_frames", ctypes.c_int64), ("cells_eval", ctypes.c_int64),
                 ("cells_nominal", ctypes.c_int64), ("workspace_bytes", ctypes.c_int64),
                 ("backptr_bytes", ctypes.c_int64), ("algorithmic_bytes", ctypes.c_int64),
-                ("kernel_launches", ctypes.c_int32), ("device", ctypes.c_int32)]
+                ("kernel_launches", ctypes.c_int32), ("device", ctypes.c_int32),
+                ("band_kernel", ctypes.c_int32), ("band_cluster", ctypes.c_int32)]
+
+BAND_KERNELS = {0: None, 1: "kab_band_kernel", 2: "kab_bandp_kernel", 3: "kab_bandq_kernel", 4: "kab_bandr_kernel"}
 
 
 class SegmentRecord(ctypes.Structure):
