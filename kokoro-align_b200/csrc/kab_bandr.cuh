@@ -53,7 +53,7 @@ struct KabBandrGeom {
 };
 __host__ __device__ inline KabBandrGeom kab_bandr_geom(int stage_bytes) {
   KabBandrGeom g;
-  g.ctrl_off = ((size_t)2 * KAB_BR_NS * 8 + 64 + 127) & ~(size_t)127;      // after the mbarriers and CTA scalars
+  g.ctrl_off = ((size_t)(2 * KAB_BR_NS + KAB_BR_CW * KAB_BR_TD) * 8 + 64 + 127) & ~(size_t)127;  // after the mbarriers and CTA scalars
   g.tile_off = g.ctrl_off + (size_t)KAB_BR_CW * 128;                       // one 128-byte control block per compute warp
   g.mbox_off = g.tile_off + (size_t)KAB_BR_CW * KAB_BR_TD * 8 * 32 * 8;    // tiles [w][TD][8 frames][32 lanes] float2
   g.bp_off = g.mbox_off + (size_t)KAB_BR_CW * KAB_BR_MD * KAB_BR_GH * 16;  // mailboxes [w][MD][12 lanes][2] (score, seq)
@@ -129,7 +129,8 @@ __global__ void __launch_bounds__(KAB_BR_THREADS, 1)
   extern __shared__ __align__(128) unsigned char kab_smem[];
   uint64_t *efull = reinterpret_cast<uint64_t *>(kab_smem);  // [NS]
   uint64_t *eempty = efull + NS;                             // [NS]
-  unsigned int *s_item = reinterpret_cast<unsigned int *>(eempty + NS);
+  uint64_t *slotfree = eempty + NS;                          // [CW][TD] tile slot t of compute warp w has been read
+  unsigned int *s_item = reinterpret_cast<unsigned int *>(slotfree + CW * TD);
   int *s_vmax = reinterpret_cast<int *>(s_item + 1);
   unsigned int *s_bad = s_item + 2;
   float *stage_base = reinterpret_cast<float *>(kab_smem + geo.stage_off);
@@ -186,6 +187,8 @@ __global__ void __launch_bounds__(KAB_BR_THREADS, 1)
     if (tid == 0) {
       *s_vmax = -1;
       *s_bad = 0u;
+      for (int k = 0; k < CW * TD; ++k) kab_mbar_init(&slotfree[k], 1);  // (everybody left them at the barrier below)
+      kab_fence_mbar_init();
     }
     if (rank == 0 && tid == 0) {
       const unsigned int it = atomicAdd(p.queue, 1u);
@@ -297,12 +300,15 @@ __global__ void __launch_bounds__(KAB_BR_THREADS, 1)
         const int g0 = c * (KAB_BR_F / G);  // first group of the chunk
         KAB_RTM(pa);
         if (own) {
-          // the slots of both tiles are free once the compute warp has finished group g0 + 1 - TD
-          const int want = min(g0 + 1, n_groups - 1) - TD + 1;
-          int tries = 0;
-          while ((int)kab_lds_relaxed_u32(ctrl + 4 * KAB_BR_C_COMPDONE) < want) {
-            if (pp == 0) service_bp();
-            if (++tries > 16) __nanosleep(32);  // (far ahead of the compute warp: stop taking its issue slots)
+          // the slots of both tiles are free once the compute warp has finished groups g0 - TD and
+          // g0 + 1 - TD: it arrives on the slot's mbarrier after every group, and this warp sleeps in
+          // mbarrier.try_wait (hardware) instead of polling shared memory -- the polling loops of the
+          // helpers were most of the instructions the SM executed
+          if (pp == 0) service_bp();
+#pragma unroll
+          for (int gi = 0; gi < KAB_BR_F / G; ++gi) {
+            const int g = g0 + gi;
+            if (g >= TD && g < n_groups) kab_mbar_wait(&slotfree[cw * TD + (g & (TD - 1))], (uint32_t)(g / TD - 1) & 1u);
           }
           kab_mbar_wait(&efull[st], ph);
         }
@@ -558,6 +564,7 @@ __global__ void __launch_bounds__(KAB_BR_THREADS, 1)
             __syncwarp();
             if (lane == 0) {
               kab_sts_relaxed_u32(ctrl + 4 * KAB_BR_C_COMPDONE, seq + 1u);
+              kab_mbar_arrive(&slotfree[cw * TD + t]);  // the tile has been read: the prep warps may reuse its slot
               if (remote_down) kab_st_cluster_u32(down_done, seq + 1u);
             }
             if (lane >= 32 - GH) publish(up_mbox + (uint32_t)(g & (MD - 1)) * (GH * 16u), seq + 1u);
@@ -665,6 +672,7 @@ __global__ void __launch_bounds__(KAB_BR_THREADS, 1)
         __syncwarp();
         if (lane == 0) {
           kab_sts_relaxed_u32(ctrl + 4 * KAB_BR_C_COMPDONE, (uint32_t)(g + 1));
+          kab_mbar_arrive(&slotfree[cw * TD + t]);
           if (remote_down) kab_st_cluster_u32(down_done, (uint32_t)(g + 1));
         }
         KAB_RTM(td);

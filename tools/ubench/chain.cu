@@ -113,7 +113,7 @@ void run(const char *name, int per_iter, int warps, int active) {
 template <int NOISE>
 __global__ void kn(float *out, long long *cyc, float e, volatile int *flag) {
   __shared__ int word;
-  __shared__ float buf[4096];
+  __shared__ __align__(16) float buf[4096];
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) word = 0;
   for (int i = threadIdx.x; i < 4096; i += blockDim.x) buf[i] = i;
