@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <new>
 #include <vector>
 
@@ -309,7 +310,7 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
   // ---- wide vocabularies: can the staged kernels work on a compact copy of the log-probs?
   // (every lattice they would take uses at most MAX_STAGE_V - 1 distinct label columns)
   std::vector<int32_t> h_gather;
-  if (V > MAX_STAGE_V && M == 4) {
+  if (V > MAX_STAGE_V && M <= 4) {
     std::vector<uint8_t> seen((size_t)V, 0);
     int64_t dmax = 0;
     bool any = false;
@@ -400,7 +401,9 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
     while (col16.size() % 8) col16.push_back(0);
     for (int k = 0; k < 8; ++k) col16.push_back(0);
 
-    const bool fast = M == 4 && !special && Veff <= MAX_STAGE_V;
+    // max_move 1 .. 3 run in the same kernels (their MM instantiations turn the excluded moves'
+    // candidates into -inf); more than four moves only exist in the generic kernel
+    const bool fast = M <= 4 && !special && Veff <= MAX_STAGE_V;
     const bool full = W >= S && (S * (T - 1)) / T <= W / 2;
     const int64_t weff = std::min<int64_t>(W, S);
     int q;
@@ -413,7 +416,7 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
     } else if (fast && W >= 1 && S <= 3 * T && weff + 32 <= KAB_BAND_OW * BAND_MAX_WARPS) {
       q = Q_BAND;  // backpointer offsets are assigned below, once the ring size is known
       max_band_weff = std::max(max_band_weff, weff);
-    } else if (fast && full && ((S + KAB_BAND_OW - 1) / KAB_BAND_OW + KAB_WD_CW - 1) / KAB_WD_CW + 1 <= wide_capacity) {
+    } else if (fast && M == 4 && full && ((S + KAB_BAND_OW - 1) / KAB_BAND_OW + KAB_WD_CW - 1) / KAB_WD_CW + 1 <= wide_capacity) {
       q = Q_WIDE;  // unbanded and wider than a CTA: a chain of warps over the whole GPU
       const int nww = (int)((S + KAB_BAND_OW - 1) / KAB_BAND_OW);
       d.k = nww;
@@ -478,7 +481,7 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
     const double est_r = std::max(max_t, sum_t / std::max(1, pl->sm_count / std::max(1, ncr))) * 108.0;
     const double est_b = std::max(max_t, sum_t / (double)(pl->sm_count * (pl->band_nw <= 16 ? 2 : 1))) * 190.0;
     const bool use_r = r_ok && want_r != 0 && want_nc != 0 && want_q != 0 && (want_r >= 1 || want_nc >= 1 || est_r <= est_b);
-    const bool use_q = !use_r && q_ok && want_q != 0 && want_nc != 0 && (want_q >= 1 || n_band <= pl->sm_count / ncq);
+    const bool use_q = !use_r && M == 4 && q_ok && want_q != 0 && want_nc != 0 && (want_q >= 1 || n_band <= pl->sm_count / ncq);
     if (use_r || use_q) {
       pl->band_q = true;
       pl->band_r = use_r;
@@ -497,7 +500,7 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
         const int64_t resident = pl->sm_count / nc;
         want_nc = (int64_t)pl->lists[Q_BAND].size() <= resident ? nc : 0;
       }
-      return cluster_ok && want_nc >= 1; }()) {
+      return M == 4 && cluster_ok && want_nc >= 1; }()) {
       pl->band_nc = std::min(8, std::max(nc, want_nc));
       const int nwt = KAB_BP_CW * pl->band_nc;
       for (KabLattice &d : pl->lists[Q_BAND]) {
@@ -588,7 +591,8 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
     // ---- launch geometry
     if (!pl->lists[Q_WARP].empty()) {
       const size_t smem = 128 + (size_t)KAB_WARPS_PER_CTA * (KAB_WARP_STAGES * pl->stage_bytes + 256);  // + label tables
-      const void *fn = Veff == 39 ? (const void *)kab_warp_kernel<39> : (const void *)kab_warp_kernel<0>;
+      const void *fn = M == 4 ? (Veff == 39 ? (const void *)kab_warp_kernel<39, false> : (const void *)kab_warp_kernel<0, false>)
+                              : (Veff == 39 ? (const void *)kab_warp_kernel<39, true> : (const void *)kab_warp_kernel<0, true>);
       if ((e = ensure_dyn_smem(fn, device, smem)) != cudaSuccess) { rc = cuda_fail(e, "cudaFuncSetAttribute(warp)"); break; }
       int occ = 0;
       if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, KAB_WARPS_PER_CTA * 32, smem)) != cudaSuccess) { rc = cuda_fail(e, "occupancy(warp)"); break; }
@@ -611,7 +615,8 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
       if ((e = pool_malloc((void **)&pl->d_band_fifo, (size_t)pl->band_fifo_bytes)) != cudaSuccess) { rc = cuda_fail(e, "pool_malloc(band FIFOs)"); break; }
       const size_t smem_b = pl->band_r ? kab_bandr_geom(pl->stage_bytes).smem_bytes
                                        : (pl->band_q ? kab_bandq_geom(pl->stage_bytes).smem_bytes : kab_bandp_geom(pl->stage_bytes).smem_bytes);
-      const void *fn = pl->band_r ? (const void *)kab_bandr_kernel : (pl->band_q ? (const void *)kab_bandq_kernel : (const void *)kab_bandp_kernel);
+      const void *fn = pl->band_r ? (M == 4 ? (const void *)kab_bandr_kernel<false> : (const void *)kab_bandr_kernel<true>)
+                                  : (pl->band_q ? (const void *)kab_bandq_kernel : (const void *)kab_bandp_kernel);
       const int threads = pl->band_r ? KAB_BR_THREADS : (pl->band_q ? KAB_BQ_THREADS : KAB_BP_THREADS);
       if ((e = ensure_dyn_smem(fn, device, smem_b)) != cudaSuccess) { rc = cuda_fail(e, "cudaFuncSetAttribute(cluster band)"); break; }
       pl->smem[Q_BAND] = smem_b;
@@ -629,7 +634,8 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
       pl->grid[Q_BAND] = ncl * pl->band_nc;
     } else if (!pl->lists[Q_BAND].empty()) {
       const KabBandGeom geo = kab_band_geom(pl->band_nw, pl->stage_bytes);
-      const void *fn = pl->band_nw <= 16 ? (const void *)kab_band_kernel<512> : (const void *)kab_band_kernel<1024>;
+      const void *fn = M == 4 ? (pl->band_nw <= 16 ? (const void *)kab_band_kernel<512, false> : (const void *)kab_band_kernel<1024, false>)
+                              : (pl->band_nw <= 16 ? (const void *)kab_band_kernel<512, true> : (const void *)kab_band_kernel<1024, true>);
       if ((e = ensure_dyn_smem(fn, device, geo.smem_bytes)) != cudaSuccess) { rc = cuda_fail(e, "cudaFuncSetAttribute(band)"); break; }
       int occ = 0;
       if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, pl->band_nw * 32, geo.smem_bytes)) != cudaSuccess) { rc = cuda_fail(e, "occupancy(band)"); break; }
@@ -690,6 +696,10 @@ int kab_plan_run_device(kab_plan *pl, const float *d_log_probs, int32_t *d_best_
   p.V = pl->V; p.W = pl->W; p.M = pl->M;
   p.stage_frames = pl->stage_frames; p.stage_bytes = pl->stage_bytes;
   p.one = 1u;
+  {  // max_move < 4: the excluded moves' candidates become -inf (kab_mm)
+    const float ninf = -std::numeric_limits<float>::infinity();
+    p.mm1 = pl->M >= 2 ? 0.0f : ninf; p.mm2 = pl->M >= 3 ? 0.0f : ninf; p.mm3 = pl->M >= 4 ? 0.0f : ninf;
+  }
   p.band_nw = pl->band_nw;
 
   // the staged kernels' view of the log-probs: the caller's array, or its compact copy
@@ -714,12 +724,15 @@ int kab_plan_run_device(kab_plan *pl, const float *d_log_probs, int32_t *d_best_
 
   if (!pl->lists[Q_WARP].empty()) {
     KabParams pw = pf; pw.queue = pl->d_queue + Q_WARP;
-    if (pf.V == 39)
-      kab_warp_kernel<39><<<pl->grid[Q_WARP], KAB_WARPS_PER_CTA * 32, pl->smem[Q_WARP], stream>>>(
-          pl->d_lists[Q_WARP], (int)pl->lists[Q_WARP].size(), pw);
-    else
-      kab_warp_kernel<0><<<pl->grid[Q_WARP], KAB_WARPS_PER_CTA * 32, pl->smem[Q_WARP], stream>>>(
-          pl->d_lists[Q_WARP], (int)pl->lists[Q_WARP].size(), pw);
+    const int nwl = (int)pl->lists[Q_WARP].size();
+    const dim3 wg((unsigned)pl->grid[Q_WARP]), wb(KAB_WARPS_PER_CTA * 32);
+    if (pl->M == 4) {
+      if (pf.V == 39) kab_warp_kernel<39, false><<<wg, wb, pl->smem[Q_WARP], stream>>>(pl->d_lists[Q_WARP], nwl, pw);
+      else kab_warp_kernel<0, false><<<wg, wb, pl->smem[Q_WARP], stream>>>(pl->d_lists[Q_WARP], nwl, pw);
+    } else {
+      if (pf.V == 39) kab_warp_kernel<39, true><<<wg, wb, pl->smem[Q_WARP], stream>>>(pl->d_lists[Q_WARP], nwl, pw);
+      else kab_warp_kernel<0, true><<<wg, wb, pl->smem[Q_WARP], stream>>>(pl->d_lists[Q_WARP], nwl, pw);
+    }
   }
   if (!pl->lists[Q_BAND].empty()) {
     KabParams pb = pf; pb.queue = pl->d_queue + Q_BAND;
@@ -856,7 +869,10 @@ int kab_plan_run_device(kab_plan *pl, const float *d_log_probs, int32_t *d_best_
         } rdbg_print{rdbg, stream, nwt};
 #endif
         if (pl->band_r) {
-          KAB_CUDA(cudaLaunchKernelEx(&cfg, kab_bandr_kernel, (const KabLattice *)pl->d_lists[Q_BAND], n_band, pb));
+          if (pl->M == 4)
+            KAB_CUDA(cudaLaunchKernelEx(&cfg, kab_bandr_kernel<false>, (const KabLattice *)pl->d_lists[Q_BAND], n_band, pb));
+          else
+            KAB_CUDA(cudaLaunchKernelEx(&cfg, kab_bandr_kernel<true>, (const KabLattice *)pl->d_lists[Q_BAND], n_band, pb));
           const dim3 fg((unsigned)n_band, (unsigned)((pl->max_T[Q_BAND] + KAB_FIN_ROWS - 1) / KAB_FIN_ROWS));
           kab_finite_rows_kernel<<<fg, 256, 0, stream>>>(pl->d_lists[Q_BAND], pf.lp, pf.V, d_status, d_final_score);
         } else
@@ -879,12 +895,17 @@ int kab_plan_run_device(kab_plan *pl, const float *d_log_probs, int32_t *d_best_
         const dim3 gg((unsigned)n_band, (unsigned)((pl->max_T[Q_BAND] + KAB_BT_GATHER_FRAMES - 1) / KAB_BT_GATHER_FRAMES));
         kab_bt_gather_kernel<<<gg, 256, 0, stream>>>(pl->d_lists[Q_BAND], pb);
       }
-    } else if (pl->band_nw <= 16)
-      kab_band_kernel<512><<<pl->grid[Q_BAND], pl->band_nw * 32, pl->smem[Q_BAND], stream>>>(
-          pl->d_lists[Q_BAND], (int)pl->lists[Q_BAND].size(), pb);
-    else
-      kab_band_kernel<1024><<<pl->grid[Q_BAND], pl->band_nw * 32, pl->smem[Q_BAND], stream>>>(
-          pl->d_lists[Q_BAND], (int)pl->lists[Q_BAND].size(), pb);
+    } else {
+      const int nbl = (int)pl->lists[Q_BAND].size();
+      const dim3 bg((unsigned)pl->grid[Q_BAND]), bb((unsigned)(pl->band_nw * 32));
+      if (pl->band_nw <= 16) {
+        if (pl->M == 4) kab_band_kernel<512, false><<<bg, bb, pl->smem[Q_BAND], stream>>>(pl->d_lists[Q_BAND], nbl, pb);
+        else kab_band_kernel<512, true><<<bg, bb, pl->smem[Q_BAND], stream>>>(pl->d_lists[Q_BAND], nbl, pb);
+      } else {
+        if (pl->M == 4) kab_band_kernel<1024, false><<<bg, bb, pl->smem[Q_BAND], stream>>>(pl->d_lists[Q_BAND], nbl, pb);
+        else kab_band_kernel<1024, true><<<bg, bb, pl->smem[Q_BAND], stream>>>(pl->d_lists[Q_BAND], nbl, pb);
+      }
+    }
 #ifdef KAB_BAND_TIMING
     {
       long long h[32 * 8];

@@ -69,7 +69,7 @@ __device__ __forceinline__ void kab_bulk_wait_read0() {
 __device__ __forceinline__ void kab_bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // MAXT: upper bound of the block size (512 -> up to 128 registers per thread, 1024 -> 64).
-template <int MAXT>
+template <int MAXT, bool MM>
 __global__ void __launch_bounds__(MAXT, 1) kab_band_kernel(const KabLattice *__restrict__ lats, int n_lat,
                                                            KabParams p) {
   constexpr int G = KAB_BAND_G, GH = KAB_BAND_GHOST, OW = KAB_BAND_OW;
@@ -222,10 +222,10 @@ __global__ void __launch_bounds__(MAXT, 1) kab_band_kernel(const KabLattice *__r
       kab_add2(s0, s1, e3, b3, b2);
       (void)t3;
       uint32_t m = 0;
-      float n0 = kab_blank_sel(t0, th1, th3, m, 1u << 0, 2u << 0, one);
-      float n1 = kab_label_sel(a0, a1, a2, a3, m, 1u << 2, 2u << 2, one);
-      float n2 = kab_blank_sel(t2, t1, th1, m, 1u << 4, 2u << 4, one);
-      float n3 = kab_label_sel(b0, b1, b2, b3, m, 1u << 6, 2u << 6, one);
+      float n0 = kab_blank_sel(t0, kab_mm<MM>(th1, p.mm1), kab_mm<MM>(th3, p.mm3), m, 1u << 0, 2u << 0, one);
+      float n1 = kab_label_sel(a0, kab_mm<MM>(a1, p.mm1), kab_mm<MM>(a2, p.mm2), kab_mm<MM>(a3, p.mm3), m, 1u << 2, 2u << 2, one);
+      float n2 = kab_blank_sel(t2, kab_mm<MM>(t1, p.mm1), kab_mm<MM>(th1, p.mm3), m, 1u << 4, 2u << 4, one);
+      float n3 = kab_label_sel(b0, kab_mm<MM>(b1, p.mm1), kab_mm<MM>(b2, p.mm2), kab_mm<MM>(b3, p.mm3), m, 1u << 6, 2u << 6, one);
       if (SLOW) {  // cells outside [lo, hi) are inactive: state vb+k is inside iff 0 <= vb+k-lo < hi-lo
         const unsigned a = (unsigned)(vb - lo), wd = (unsigned)(hi - lo);
         n0 = (a + 0u < wd) ? n0 : ninf;

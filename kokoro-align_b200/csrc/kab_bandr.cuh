@@ -120,6 +120,7 @@ __device__ __forceinline__ void kab_fence_cta() { asm volatile("fence.acq_rel.ct
 #define KAB_RTM_ADD(acc, a, b)
 #endif
 
+template <bool MM>
 __global__ void __launch_bounds__(KAB_BR_THREADS, 1)
     kab_bandr_kernel(const KabLattice *__restrict__ lats, int n_lat, KabParams p) {
   constexpr int G = KAB_BAND_G, GH = KAB_BR_GH, OW = KAB_BR_OW;
@@ -420,8 +421,8 @@ __global__ void __launch_bounds__(KAB_BR_THREADS, 1)
         const float th3 = __fadd_rn(h3, xb);  // vb - 3 (move 3)
         kab_add2(s0, s1, x1, a1, a0);         // label <- vb + 1 (move 0), vb (move 1)
         kab_add2(h2, h1, x1, a3, a2);         //       <- vb - 1 (move 2), vb - 2 (move 3)
-        const float m0 = kab_blank_sel(t0, th1, th3, bw, 1u << (sh + 0), 2u << (sh + 0), one);
-        const float m1 = kab_label_sel(a0, a1, a2, a3, bw, 1u << (sh + 2), 2u << (sh + 2), one);
+        const float m0 = kab_blank_sel(t0, kab_mm<MM>(th1, p.mm1), kab_mm<MM>(th3, p.mm3), bw, 1u << (sh + 0), 2u << (sh + 0), one);
+        const float m1 = kab_label_sel(a0, kab_mm<MM>(a1, p.mm1), kab_mm<MM>(a2, p.mm2), kab_mm<MM>(a3, p.mm3), bw, 1u << (sh + 2), 2u << (sh + 2), one);
         s0 = m0; s1 = m1;
       };
       // mailboxes: mine (messages of the warp below), and the one of the warp above -- in this CTA,

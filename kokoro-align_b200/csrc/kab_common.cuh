@@ -46,7 +46,17 @@ struct KabParams {
                             // here ([B]) and leave the traceback to kab_btpar.cuh
   long long *debug;         // development only (KAB_BAND_TIMING builds)
   uint32_t one;             // the value 1, opaque to the compiler (kab_blank_sel / kab_label_sel)
+  float mm1, mm2, mm3;      // max_move < 4 (the MM instantiations of the staged kernels): 0 or -inf, added to the
+                            // candidates of moves 1 / 2 / 3 -- a candidate that max_move excludes (align.py:70)
+                            // becomes -inf, which is what "no candidate" is everywhere else
 };
+
+// max_move < 4 in the kernels written for four moves: x + 0.0f == x for every candidate (finite or
+// -inf, never -0), x + -inf == -inf.  MM == false (max_move 4): nothing is emitted.
+template <bool MM>
+__device__ __forceinline__ float kab_mm(const float cand, const float mask) {
+  return MM ? __fadd_rn(cand, mask) : cand;
+}
 
 __device__ __forceinline__ float kab_neg_inf() { return __int_as_float(0xff800000); }
 __device__ __forceinline__ bool kab_finite(float x) { return fabsf(x) < __int_as_float(0x7f800000); }

@@ -39,10 +39,10 @@ struct KabWarpCfg {
 // bits [shift, shift + 2K).  s[] holds frame i-1 on entry and frame i on return.
 // Lane 0 is a dummy whose states are permanently -inf ("states -K..-1"), so the halo of lane 1
 // (state 0's lower neighbours) is -inf without any select.
-template <int K>
+template <int K, bool MM>
 __device__ __forceinline__ void kab_warp_frame(float (&s)[K], const float eb, const float (&el)[K / 2],
                                                const bool lane1, uint32_t &w, const int shift,
-                                               const uint32_t one) {
+                                               const uint32_t one, const float mm1, const float mm2, const float mm3) {
   float h1, h2, h3;  // previous-frame scores of states K*(lane-1)-1, -2, -3
   if (K >= 4) {
     h1 = __shfl_up_sync(KAB_FULL_MASK, s[K - 1], 1);
@@ -66,20 +66,20 @@ __device__ __forceinline__ void kab_warp_frame(float (&s)[K], const float eb, co
     // blank state kb: moves 0, 1, 3
     const float b1 = kb >= 1 ? t[kb >= 1 ? kb - 1 : 0] : th1;
     const float b3 = kb >= 3 ? t[kb >= 3 ? kb - 3 : 0] : (kb == 2 ? th1 : th3);
-    n[kb] = kab_blank_sel(t[kb], b1, b3, w, 1u << (shift + 2 * kb), 2u << (shift + 2 * kb), one);
+    n[kb] = kab_blank_sel(t[kb], kab_mm<MM>(b1, mm1), kab_mm<MM>(b3, mm3), w, 1u << (shift + 2 * kb), 2u << (shift + 2 * kb), one);
     // label state kl: moves 0..3 = states (kl, kl-1) and (kl-2, kl-3), both (even, odd) pairs
     float a0, a1, a2, a3;
     kab_add2(s[kl - 1], s[kl], el[q], a1, a0);
     if (q >= 1) kab_add2(s[q >= 1 ? kl - 3 : 0], s[q >= 1 ? kl - 2 : 0], el[q], a3, a2);
     else kab_add2(h2, h1, el[q], a3, a2);
-    n[kl] = kab_label_sel(a0, a1, a2, a3, w, 1u << (shift + 2 * kl), 2u << (shift + 2 * kl), one);
+    n[kl] = kab_label_sel(a0, kab_mm<MM>(a1, mm1), kab_mm<MM>(a2, mm2), kab_mm<MM>(a3, mm3), w, 1u << (shift + 2 * kl), 2u << (shift + 2 * kl), one);
   }
 #pragma unroll
   for (int k = 0; k < K; ++k) s[k] = n[k];
 }
 
 // VCT: compile-time vocabulary (39) or 0 = runtime p.V.
-template <int K, int VCT>
+template <int K, int VCT, bool MM>
 __device__ void kab_warp_align(const KabLattice &lat, const KabParams &p, float *stage_base, uint64_t *bars,
                                uint16_t *labtab, const uint64_t policy, uint32_t &chunk_counter, const int lane) {
   using Cfg = KabWarpCfg<K>;
@@ -93,6 +93,7 @@ __device__ void kab_warp_align(const KabLattice &lat, const KabParams &p, float 
   uint32_t *bpw = reinterpret_cast<uint32_t *>(p.bp + lat.bp_off);
   const bool lane0 = lane == 0, lane1 = lane == 1;
   const uint32_t one = p.one;  // runtime 1 (see kab_blank_sel)
+  const float mm1 = p.mm1, mm2 = p.mm2, mm3 = p.mm3;
   const int sbase = K * (lane - 1);  // first state of this lane (lane 0: dummy, all -inf)
 
   // byte offsets (col * 4) of this lane's K/2 label states inside an emission row
@@ -178,7 +179,7 @@ __device__ void kab_warp_align(const KabLattice &lat, const KabParams &p, float 
         float el[K / 2];
 #pragma unroll
         for (int q = 0; q < K / 2; ++q) el[q] = *reinterpret_cast<const float *>(rb + coff[q]);
-        kab_warp_frame<K>(s, eb, el, lane1, word, f * BPF, one);
+        kab_warp_frame<K, MM>(s, eb, el, lane1, word, f * BPF, one, mm1, mm2, mm3);
       }
       *bprow = word;
       bprow += 32;
@@ -193,7 +194,7 @@ __device__ void kab_warp_align(const KabLattice &lat, const KabParams &p, float 
 #pragma unroll
         for (int q = 0; q < K / 2; ++q) el[q] = *reinterpret_cast<const float *>(rowb + coff[q]);
         uint32_t fw = 0;
-        kab_warp_frame<K>(s, eb, el, lane1, fw, 0, one);
+        kab_warp_frame<K, MM>(s, eb, el, lane1, fw, 0, one, mm1, mm2, mm3);
         word |= fw << (f * BPF);
       }
       *bprow = word;
@@ -287,7 +288,7 @@ __device__ void kab_warp_align(const KabLattice &lat, const KabParams &p, float 
   if (pend_t >= 0) out_sc[pend_t] = pend_s;
 }
 
-template <int VCT>
+template <int VCT, bool MM>
 __global__ void __launch_bounds__(KAB_WARPS_PER_CTA * 32, KAB_WARP_MINBLOCKS)
     kab_warp_kernel(const KabLattice *__restrict__ lats, int n_lat, KabParams p) {
   extern __shared__ __align__(128) unsigned char kab_smem[];
@@ -317,10 +318,10 @@ __global__ void __launch_bounds__(KAB_WARPS_PER_CTA * 32, KAB_WARP_MINBLOCKS)
     if (item >= (unsigned int)n_lat) break;
     const KabLattice lat = lats[item];
     switch (lat.k) {
-      case 2: kab_warp_align<2, VCT>(lat, p, stage_base, bars, labtab, policy, chunk_counter, lane); break;
-      case 4: kab_warp_align<4, VCT>(lat, p, stage_base, bars, labtab, policy, chunk_counter, lane); break;
-      case 6: kab_warp_align<6, VCT>(lat, p, stage_base, bars, labtab, policy, chunk_counter, lane); break;
-      default: kab_warp_align<8, VCT>(lat, p, stage_base, bars, labtab, policy, chunk_counter, lane); break;
+      case 2: kab_warp_align<2, VCT, MM>(lat, p, stage_base, bars, labtab, policy, chunk_counter, lane); break;
+      case 4: kab_warp_align<4, VCT, MM>(lat, p, stage_base, bars, labtab, policy, chunk_counter, lane); break;
+      case 6: kab_warp_align<6, VCT, MM>(lat, p, stage_base, bars, labtab, policy, chunk_counter, lane); break;
+      default: kab_warp_align<8, VCT, MM>(lat, p, stage_base, bars, labtab, policy, chunk_counter, lane); break;
     }
     __syncwarp();
   }

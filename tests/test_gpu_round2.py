@@ -363,3 +363,35 @@ def test_encoder_handoff_stays_on_device(kab):
     out2 = kab.best_path_from_logits_tensor(d_logits, labels)
     np.testing.assert_array_equal(out2["best_path"].cpu().numpy(), path)
     assert d_logits.cpu().numpy().tobytes() == lp_dev.tobytes()
+
+
+# ------------------------------------------------------------------ non-default keywords in the staged kernels
+@pytest.mark.parametrize("max_move", [1, 2, 3])
+@pytest.mark.parametrize("band_env", [{}, {"KAB_BAND_CLUSTER": "0"}])
+def test_max_move_below_four_in_staged_kernels(kab, monkeypatch, max_move, band_env):
+    """align.py:43's `max_move` keyword at 1, 2, 3: same warp / band kernels (their MM instantiations
+    turn the candidates of the excluded moves into -inf), not the generic kernel; bit-exact against
+    the C oracle, tie stress included; dead bands (max_move 1 cannot leave state 0) keep status 1."""
+    from kokoro_align_b200 import synth
+    from oracle import ctc_oracle
+    for k, v in band_env.items():
+        monkeypatch.setenv(k, v)
+    T = np.array([300, 861, 120, 5000, 2500, 9, 700])
+    L = np.array([20, 60, 3, 350, 400, 1, 0])       # sparse transcripts: the path can end at S-1 without long jumps
+    lp, t_off, labels, l_off = synth.make_batch(T, L, seed=9950 + max_move, planted=True)
+    lp[: int(t_off[2])] = (np.round(lp[: int(t_off[2])] * 2) / 2).astype(np.float32)   # ties in the first two lattices
+    ref = ctc_oracle.ctc_best_path_batch(lp, t_off, labels, l_off, 1000, max_move, n_threads=4)
+    with kab.AlignPlan(t_off, labels, l_off, 39, 1000, max_move) as plan:
+        got = plan.run_host(lp)
+        assert plan.info.n_class[2] == 0, "max_move < 4 must not fall back to the generic kernel"
+        assert plan.info.n_class[0] >= 4 and plan.info.n_class[1] >= 2
+    path, labs, scores, final, status = got
+    rp, rl, rs, rf, rst = ref
+    np.testing.assert_array_equal(status, rst)
+    for b in range(len(T)):
+        if rst[b] != 0:
+            continue
+        a, e = int(t_off[b]), int(t_off[b + 1])
+        np.testing.assert_array_equal(path[a:e], rp[a:e], err_msg=f"lattice {b}")
+        assert scores[a:e].tobytes() == rs[a:e].tobytes() and final[b].tobytes() == rf[b].tobytes()
+    assert (rst == 0).sum() >= (5 if max_move >= 2 else 1)
