@@ -111,6 +111,9 @@ __device__ __forceinline__ uint32_t kab_ld_cluster_u32(uint32_t addr) {
   return v;
 }
 __device__ __forceinline__ void kab_fence_cta() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
+__device__ __forceinline__ void kab_mbar_arrive_addr(uint32_t bar) {  // (32-bit shared address: no conversion per call)
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 
 #ifdef KAB_BANDR_TIMING
 #define KAB_RTM(var) const long long var = clock64()
@@ -474,6 +477,9 @@ __global__ void __launch_bounds__(KAB_BR_THREADS, 1)
       const long long tm_start = clock64();
 #endif
       static_assert((TD & (TD - 1)) == 0 && (MD & (MD - 1)) == 0, "ring indices are masks");
+      const uint32_t tiles_lane = smem0 + (uint32_t)geo.tile_off + (uint32_t)cw * (TD * 2048u) + (uint32_t)lane * 8u;
+      const uint32_t slotfree_u32 = smem0 + (uint32_t)((2 * NS + cw * TD) * 8);  // &slotfree[cw * TD]
+      const int last_common = n_groups - 2;  // the groups 1 .. n_groups - 2 can take the common path
       for (int g = 0; g < n_groups; ++g) {
         // ---- COMMON PATH: every group but the first, the last, a (re)join of the chain and the rare
         // waits for mailbox room / a backpointer buffer.  Straight-line code with two inline polls (tile
@@ -481,7 +487,7 @@ __global__ void __launch_bounds__(KAB_BR_THREADS, 1)
         // block and the general body below has a dozen of them, and in a chain that runs at its minimal
         // lag EVERY group of every follower arrives just before its message, so the polls must not
         // divert into the general body either.
-        if (g > 0 && (g + 1) * G < T && (g < MD || up_done_seen >= (uint32_t)(g - MD + 2)) &&
+        if ((unsigned)(g - 1) < (unsigned)last_common && (g < MD || up_done_seen >= (uint32_t)(g - MD + 2)) &&
             !(gib == 0 && blk >= KAB_BR_NBB && bp_free < (uint32_t)(blk - KAB_BR_NBB + 1))) {
           KAB_RTM(fa);
 #ifdef KAB_BANDR_TIMING
@@ -505,11 +511,13 @@ __global__ void __launch_bounds__(KAB_BR_THREADS, 1)
           const long long fa2 = clock64();
 #endif
           if (!need || was_needed) {
-            const float2 *tile = reinterpret_cast<const float2 *>(kab_smem + geo.tile_off + (size_t)cw * (TD * 2048) + (size_t)t * 2048) + lane;
+            // (addresses from the 32-bit shared-window bases computed once: a generic-to-shared
+            // conversion in here costs an S2UR + ULEA on the path to the first frame)
+            const uint32_t tl = tiles_lane + (uint32_t)t * 2048u;
             float2 e[G];
 #pragma unroll
             for (int f = 0; f < G; ++f)
-              asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(e[f].x), "=f"(e[f].y) : "r"(kab_smem_u32(tile + f * 32)) : "memory");
+              asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(e[f].x), "=f"(e[f].y) : "r"(tl + f * 256) : "memory");
             tw = kab_lds_relaxed_u32(ctrl + 4 * (KAB_BR_C_TILESEQ + ((t + 1) & (TD - 1))));
             const uint32_t up_done_now = read_up_done();  // (used after the frames: mailbox room without a wait)
 #ifdef KAB_BANDR_TIMING
@@ -565,7 +573,7 @@ __global__ void __launch_bounds__(KAB_BR_THREADS, 1)
             __syncwarp();
             if (lane == 0) {
               kab_sts_relaxed_u32(ctrl + 4 * KAB_BR_C_COMPDONE, seq + 1u);
-              kab_mbar_arrive(&slotfree[cw * TD + t]);  // the tile has been read: the prep warps may reuse its slot
+              kab_mbar_arrive_addr(slotfree_u32 + (uint32_t)t * 8u);  // the tile has been read: the prep warps may reuse its slot
               if (remote_down) kab_st_cluster_u32(down_done, seq + 1u);
             }
             if (lane >= 32 - GH) publish(up_mbox + (uint32_t)(g & (MD - 1)) * (GH * 16u), seq + 1u);
