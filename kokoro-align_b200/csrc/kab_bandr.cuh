@@ -43,7 +43,10 @@
 #define KAB_BR_F 16           // frames per emission stage this kernel is built for (two groups; the plan checks it)
 #define KAB_BR_TD 8           // emission tiles per compute warp (groups the prep warps may run ahead)
 #define KAB_BR_MD 16          // mailbox depth (messages)
-#define KAB_BR_LAG 2          // a warp joining the chain lets its lower neighbour get this many groups ahead
+#ifndef KAB_BR_LAG
+#define KAB_BR_LAG 0          // a warp joining the chain lets its lower neighbour get this many groups ahead
+#endif                        // (0: it joins at once, through the common path -- every group of start-up lag is
+                              // paid again at EVERY change of the head, i.e. (18 + lag) / 18 on the whole lattice)
 #define KAB_BR_BG 16          // groups per backpointer block (2 KB)
 #define KAB_BR_NBB 4          // backpointer staging buffers per compute warp
 #define KAB_BR_THREADS ((3 * KAB_BR_CW + 1) * 32)
@@ -510,7 +513,7 @@ __global__ void __launch_bounds__(KAB_BR_THREADS, 1)
 #ifdef KAB_BANDR_TIMING
           const long long fa2 = clock64();
 #endif
-          if (!need || was_needed) {
+          if (KAB_BR_LAG == 0 || !need || was_needed) {
             // (addresses from the 32-bit shared-window bases computed once: a generic-to-shared
             // conversion in here costs an S2UR + ULEA on the path to the first frame)
             const uint32_t tl = tiles_lane + (uint32_t)t * 2048u;
@@ -636,7 +639,7 @@ __global__ void __launch_bounds__(KAB_BR_THREADS, 1)
 #endif
           if (need) {
             if (!owned) {
-              if (!was_needed) {  // (re)joining the chain: let the warp below get KAB_BR_LAG groups ahead
+              if (KAB_BR_LAG > 1 && !was_needed) {  // (re)joining the chain: let the warp below get KAB_BR_LAG groups ahead
                 const int mt = min(g - 1 + KAB_BR_LAG - 1, n_groups - 2);
                 const uint32_t ls = inbox + (uint32_t)(mt % MD) * (GH * 16u);
                 while (kab_lds_relaxed_b64(ls + 8).y != (uint32_t)(mt + 1)) __nanosleep(200);  // (a long wait: the
