@@ -43,10 +43,6 @@
 #define KAB_BR_F 16           // frames per emission stage this kernel is built for (two groups; the plan checks it)
 #define KAB_BR_TD 8           // emission tiles per compute warp (groups the prep warps may run ahead)
 #define KAB_BR_MD 16          // mailbox depth (messages)
-#ifndef KAB_BR_LAG
-#define KAB_BR_LAG 0          // a warp joining the chain lets its lower neighbour get this many groups ahead
-#endif                        // (0: it joins at once, through the common path -- every group of start-up lag is
-                              // paid again at EVERY change of the head, i.e. (18 + lag) / 18 on the whole lattice)
 #define KAB_BR_BG 16          // groups per backpointer block (2 KB)
 #define KAB_BR_NBB 4          // backpointer staging buffers per compute warp
 #define KAB_BR_THREADS ((3 * KAB_BR_CW + 1) * 32)
@@ -467,41 +463,39 @@ __global__ void __launch_bounds__(KAB_BR_THREADS, 1)
       };
       const uint32_t inbox = mbox + (uint32_t)(lane < GH ? lane : 0) * 16u;
       uint32_t up_done_seen = 0;  // groups the warp above is known to have finished
-      bool was_needed = false;    // the previous group read its message (the warp is inside the chain)
       uint2 pf0 = make_uint2(0, 0), pf1 = pf0;  // message g-1, loaded a group early
       uint32_t tw = kab_lds_relaxed_u32(ctrl + 4 * KAB_BR_C_TILESEQ);  // tile word of group 0
-      int gib = 0, blk = 0;       // group inside the current backpointer block, block index
       uint32_t bp_free = 0;       // backpointer blocks whose staging buffer is known to be free
 #ifdef KAB_BANDR_TIMING
       long long tm_tile = 0, tm_msg = 0, tm_frames = 0, tm_pub = 0, tm_bp = 0, n_need = 0, tm_wait = 0, tm_fast = 0, n_fast = 0;
-      long long cat_t[2] = {0, 0}, cat_n[2] = {0, 0}, cat_w[2] = {0, 0};
-      long long hd_tile = 0, hd_frames = 0, hd_pre = 0, hd_total = 0, hd_n = 0;
-      long long why_t[5] = {0, 0, 0, 0, 0}, why_n[5] = {0, 0, 0, 0, 0};
       const long long tm_start = clock64();
 #endif
-      static_assert((TD & (TD - 1)) == 0 && (MD & (MD - 1)) == 0, "ring indices are masks");
+      static_assert((TD & (TD - 1)) == 0 && (MD & (MD - 1)) == 0 && (BG & (BG - 1)) == 0 && (KAB_BR_NBB & (KAB_BR_NBB - 1)) == 0,
+                    "ring indices are masks");
+      // (32-bit shared-window addresses computed once: a generic-to-shared conversion inside the loop
+      // costs an S2UR + ULEA on the path to the first frame)
       const uint32_t tiles_lane = smem0 + (uint32_t)geo.tile_off + (uint32_t)cw * (TD * 2048u) + (uint32_t)lane * 8u;
       const uint32_t slotfree_u32 = smem0 + (uint32_t)((2 * NS + cw * TD) * 8);  // &slotfree[cw * TD]
+      const uint32_t bpst_lane = bpst + (uint32_t)lane * 4u;  // group g's word: + (g mod (NBB * BG)) * 128
+      // end-of-group stores as predicated instructions (no divergent blocks): per-lane flags
+      const uint32_t f_l0 = lane == 0, f_dn = lane == 0 && remote_down;
+      const uint32_t f_pl = lane >= 32 - GH && !remote_up, f_pr = lane >= 32 - GH && remote_up;
       const int last_common = n_groups - 2;  // the groups 1 .. n_groups - 2 can take the common path
+      int room_until = MD - 2;               // ... while the mailbox above is known to have room: g <= room_until
       for (int g = 0; g < n_groups; ++g) {
-        // ---- COMMON PATH: every group but the first, the last, a (re)join of the chain and the rare
-        // waits for mailbox room / a backpointer buffer.  Straight-line code with two inline polls (tile
-        // word, neighbour's message): a lone warp pays ~15 cycles of branch latency per conditional
-        // block and the general body below has a dozen of them, and in a chain that runs at its minimal
-        // lag EVERY group of every follower arrives just before its message, so the polls must not
-        // divert into the general body either.
-        if ((unsigned)(g - 1) < (unsigned)last_common && (g < MD || up_done_seen >= (uint32_t)(g - MD + 2)) &&
-            !(gib == 0 && blk >= KAB_BR_NBB && bp_free < (uint32_t)(blk - KAB_BR_NBB + 1))) {
-          KAB_RTM(fa);
-#ifdef KAB_BANDR_TIMING
-          if (lane == 0 && p.debug && g < 16384) {
-            unsigned long long gt;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-            p.debug[64 * 26 + ((size_t)gw * 16384 + g) * 2] = (long long)gt;
-          }
-#endif
+        // ---- COMMON PATH: every group but the first, the last and the rare wait for mailbox room.
+        // Straight-line code: a lone warp pays ~15 cycles per conditional block and 4-5 per dependent
+        // instruction, and in a chain that runs at its minimal lag EVERY group of every follower
+        // arrives just before its message, so the two polls (tile word, neighbour's message) are inline
+        // and the end-of-group stores are predicated.  A warp (re)joining the chain -- its ring slots
+        // recycled above the window -- comes through here too and simply waits for its first message:
+        // any start-up lag it were given is paid again at EVERY change of the head, i.e. every 18
+        // groups ((18 + lag) / 18 on the whole lattice; measured with a trace of group start times:
+        // two groups of intended lag plus the slow general body cost 6 groups per change, 8.4 -> 6.6 ms).
+        if ((unsigned)(g - 1) < (unsigned)min(last_common, room_until)) {
           const uint32_t seq = (uint32_t)g;
           const int t = g & (TD - 1);
+          KAB_RTM(fa);
 #ifndef KAB_BR_EXP_NOTILEWAIT
           while ((tw & 0x7fffffffu) != seq + 1u) tw = kab_lds_relaxed_u32(ctrl + 4 * (KAB_BR_C_TILESEQ + t));
 #endif
@@ -510,99 +504,81 @@ __global__ void __launch_bounds__(KAB_BR_THREADS, 1)
 #else
           const bool need = (tw >> 31) != 0u;
 #endif
-#ifdef KAB_BANDR_TIMING
-          const long long fa2 = clock64();
-#endif
-          if (KAB_BR_LAG == 0 || !need || was_needed) {
-            // (addresses from the 32-bit shared-window bases computed once: a generic-to-shared
-            // conversion in here costs an S2UR + ULEA on the path to the first frame)
-            const uint32_t tl = tiles_lane + (uint32_t)t * 2048u;
-            float2 e[G];
+          const uint32_t tl = tiles_lane + (uint32_t)t * 2048u;
+          float2 e[G];
 #pragma unroll
-            for (int f = 0; f < G; ++f)
-              asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(e[f].x), "=f"(e[f].y) : "r"(tl + f * 256) : "memory");
-            tw = kab_lds_relaxed_u32(ctrl + 4 * (KAB_BR_C_TILESEQ + ((t + 1) & (TD - 1))));
-            const uint32_t up_done_now = read_up_done();  // (used after the frames: mailbox room without a wait)
-#ifdef KAB_BANDR_TIMING
-            const long long fw0 = clock64();
-#endif
-#ifdef KAB_BR_TRACE2
-            long long tr_t0 = 0; int tr_polls = 0;
-            if (g >= 5000 && g < 5256) tr_t0 = clock64();
-#endif
-            if (need) {  // ghost lanes: the lower neighbour's top 24 states (message g-1, loaded a group ago)
-              const uint32_t slot = inbox + (uint32_t)((g - 1) & (MD - 1)) * (GH * 16u);
-              while (!__all_sync(KAB_FULL_MASK, owned || (pf0.y == seq && pf1.y == seq))) {
-                pf0 = kab_lds_relaxed_b64(slot);
-                pf1 = kab_lds_relaxed_b64(slot + 8);
-#ifdef KAB_BR_TRACE2
-                ++tr_polls;
-#endif
-              }
-            }
-#ifdef KAB_BR_TRACE2
-            if (g >= 5000 && g < 5256 && lane == 0 && p.debug) {
-              long long *d = p.debug + ((size_t)gw * 256 + (g - 5000)) * 4;
-              d[0] = tr_t0; d[1] = clock64(); d[2] = (need ? 1 : 0) + 2 * tr_polls;
-            }
-#endif
-#ifdef KAB_BANDR_TIMING
-            const long long fw1 = clock64();
-#endif
-            if (!owned) {
-              s0 = need ? __uint_as_float(pf0.x) : ninf;
-              s1 = need ? __uint_as_float(pf1.x) : ninf;
-            }
-            was_needed = need;
-            {
-              const uint32_t slot = inbox + (uint32_t)(g & (MD - 1)) * (GH * 16u);
+          for (int f = 0; f < G; ++f)
+            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(e[f].x), "=f"(e[f].y) : "r"(tl + f * 256) : "memory");
+          tw = kab_lds_relaxed_u32(ctrl + 4 * (KAB_BR_C_TILESEQ + ((t + 1) & (TD - 1))));
+          const uint32_t up_done_now = read_up_done();  // (used after the frames: mailbox room without a wait)
+          KAB_RTM(fw0);
+          {  // ghost lanes: the lower neighbour's top 24 states (message g-1, loaded a group ago)
+            const uint32_t slot = inbox + (uint32_t)((g - 1) & (MD - 1)) * (GH * 16u);
+            while (!__all_sync(KAB_FULL_MASK, owned || !need || (pf0.y == seq && pf1.y == seq))) {
               pf0 = kab_lds_relaxed_b64(slot);
               pf1 = kab_lds_relaxed_b64(slot + 8);
             }
-            bw = 0;
-#ifdef KAB_BANDR_TIMING
-            const long long ff0 = clock64();
-#endif
+          }
+          KAB_RTM(fw1);
+          if (!owned) {
+            s0 = need ? __uint_as_float(pf0.x) : ninf;
+            s1 = need ? __uint_as_float(pf1.x) : ninf;
+          }
+          {
+            const uint32_t slot = inbox + (uint32_t)(g & (MD - 1)) * (GH * 16u);
+            pf0 = kab_lds_relaxed_b64(slot);
+            pf1 = kab_lds_relaxed_b64(slot + 8);
+          }
+          bw = 0;
+          KAB_RTM(ff0);
 #ifdef KAB_BR_EXP_NOFRAMES
-            s0 += e[0].x + e[7].y; s1 += e[3].x;
+          s0 += e[0].x + e[7].y; s1 += e[3].x;
 #else
 #pragma unroll
-            for (int f = 0; f < G; ++f) frame(e[f].x, e[f].y, 4 * f);
+          for (int f = 0; f < G; ++f) frame(e[f].x, e[f].y, 4 * f);
 #endif
-#ifdef KAB_BANDR_TIMING
-            { const long long ff1 = clock64(); tm_frames += ff1 - ff0; tm_tile += fa2 - fa;
-              if (!need) { hd_tile += fa2 - fa; hd_frames += ff1 - ff0; hd_pre += ff0 - fa2; } }
-#endif
+          KAB_RTM(ff1);
+          // message g first (the warp above is waiting for it), then: group g is finished, its tile
+          // has been read (the prep warps may reuse the slot), progress for the warp below
+          asm volatile(
+              "{\n\t.reg .pred p0, p1, p2, p3;\n\t.reg .b64 q0, q1;\n\t"
+              "setp.ne.u32 p2, %2, 0;\n\t"
+              "setp.ne.u32 p3, %3, 0;\n\t"
+              "setp.ne.u32 p0, %0, 0;\n\t"
+              "setp.ne.u32 p1, %1, 0;\n\t"
+              "mov.b64 q0, {%9, %5};\n\t"
+              "mov.b64 q1, {%10, %5};\n\t"
+              "@p2 st.shared.v2.b32 [%8], {%9, %5};\n\t"
+              "@p2 st.shared.v2.b32 [%8+8], {%10, %5};\n\t"
+              "@p3 st.relaxed.cluster.shared::cluster.b64 [%8], q0;\n\t"
+              "@p3 st.relaxed.cluster.shared::cluster.b64 [%8+8], q1;\n\t"
+              "@p0 st.relaxed.cluster.shared::cta.u32 [%4], %5;\n\t"
+              "@p0 mbarrier.arrive.shared::cta.b64 _, [%6];\n\t"
+              "@p1 st.shared::cluster.u32 [%7], %5;\n\t}" ::"r"(f_l0),
+              "r"(f_dn), "r"(f_pl), "r"(f_pr), "r"(ctrl + 4 * KAB_BR_C_COMPDONE), "r"(seq + 1u), "r"(slotfree_u32 + (uint32_t)t * 8u),
+              "r"(down_done), "r"(up_mbox + (uint32_t)(g & (MD - 1)) * (GH * 16u)), "r"(__float_as_uint(s0)), "r"(__float_as_uint(s1))
+              : "memory");
+          asm volatile("st.shared.u32 [%0], %1;" ::"r"(bpst_lane + (uint32_t)(g & (KAB_BR_NBB * BG - 1)) * 128u), "r"(bw) : "memory");
+          up_done_seen = max(up_done_seen, up_done_now);
+          room_until = (int)up_done_seen + MD - 2;
+          if ((g & (BG - 1)) == BG - 1) {  // the block is complete: hand it to the prep warp's bulk store
+            kab_fence_proxy_async_smem();
+            kab_fence_cta();
             __syncwarp();
-            if (lane == 0) {
-              kab_sts_relaxed_u32(ctrl + 4 * KAB_BR_C_COMPDONE, seq + 1u);
-              kab_mbar_arrive_addr(slotfree_u32 + (uint32_t)t * 8u);  // the tile has been read: the prep warps may reuse its slot
-              if (remote_down) kab_st_cluster_u32(down_done, seq + 1u);
-            }
-            if (lane >= 32 - GH) publish(up_mbox + (uint32_t)(g & (MD - 1)) * (GH * 16u), seq + 1u);
-#ifdef KAB_BR_TRACE2
-            if (g >= 5000 && g < 5256 && lane == 0 && p.debug) p.debug[((size_t)gw * 256 + (g - 5000)) * 4 + 3] = clock64();
-#endif
-            asm volatile("st.shared.u32 [%0], %1;" ::"r"(bpst + (uint32_t)((blk & (KAB_BR_NBB - 1)) * BG + gib) * 128u + (uint32_t)lane * 4u), "r"(bw) : "memory");
-            up_done_seen = max(up_done_seen, up_done_now);
-            if (++gib == BG) {  // the block is complete: hand it to the prep warp's bulk store
-              kab_fence_proxy_async_smem();
-              kab_fence_cta();
-              __syncwarp();
-              ++blk;
-              gib = 0;
-              if (lane == 0) kab_sts_relaxed_u32(ctrl + 4 * KAB_BR_C_BPREADY, (uint32_t)blk);
-              bp_free = kab_lds_relaxed_u32(ctrl + 4 * KAB_BR_C_BPFREE);
-            }
-#ifdef KAB_BANDR_TIMING
-            if (lane == 0 && p.debug && g < 16384) p.debug[64 * 26 + ((size_t)gw * 16384 + g) * 2 + 1] = (fw1 - fw0) * 4 + (need ? 1 : 0);
-            { const long long fb = clock64(); tm_fast += fb - fa; ++n_fast; cat_t[need] += fb - fa; cat_n[need] += 1; n_need += need;
-              tm_wait += fw1 - fw0; cat_w[need] += fw1 - fw0;
-              if (!need) { hd_total += fb - fa; ++hd_n; } }
-#endif
-            continue;
+            const int blk = (g >> 4) + 1;  // blocks finished
+            static_assert(BG == 16, "g >> 4");
+            if (lane == 0) kab_sts_relaxed_u32(ctrl + 4 * KAB_BR_C_BPREADY, (uint32_t)blk);
+            // the next block's buffer (that of block blk - NBB) must have left shared memory: the
+            // prep warp issued that store 48 groups ago, so this does not wait
+            if (blk >= KAB_BR_NBB)
+              while (bp_free < (uint32_t)(blk - KAB_BR_NBB + 1)) bp_free = kab_lds_relaxed_u32(ctrl + 4 * KAB_BR_C_BPFREE);
           }
+#ifdef KAB_BANDR_TIMING
+          { const long long fb = clock64(); tm_fast += fb - fa; ++n_fast; n_need += need; tm_wait += fw1 - fw0; tm_frames += ff1 - ff0; tm_tile += fw0 - fa; }
+#endif
+          continue;
         }
+        const int gib = g & (BG - 1), blk = g / BG;  // group inside its backpointer block, block index
         const int i0 = g * G, nfr = min(G, T - i0);
         const bool more = i0 + G < T;
         const int t = g % TD;
@@ -614,8 +590,6 @@ __global__ void __launch_bounds__(KAB_BR_THREADS, 1)
           p.debug[64 * 26 + ((size_t)gw * 16384 + g) * 2] = (long long)gt;
           p.debug[64 * 26 + ((size_t)gw * 16384 + g) * 2 + 1] = 2;
         }
-        const int why = g == 0 ? 0 : (!((g + 1) * G < T) ? 1 : (!(g < MD || up_done_seen >= (uint32_t)(g - MD + 2)) ? 2 :
-                        ((gib == 0 && blk >= KAB_BR_NBB && bp_free < (uint32_t)(blk - KAB_BR_NBB + 1)) ? 3 : 4)));
 #endif
         // ---- this group's tile (its word was loaded during the previous group)
         while ((tw & 0x7fffffffu) != (uint32_t)(g + 1)) tw = kab_lds_relaxed_u32(ctrl + 4 * (KAB_BR_C_TILESEQ + t));
@@ -629,9 +603,6 @@ __global__ void __launch_bounds__(KAB_BR_THREADS, 1)
         if (more) tw = kab_lds_relaxed_u32(ctrl + 4 * (KAB_BR_C_TILESEQ + (t + 1 == TD ? 0 : t + 1)));
         KAB_RTM(tb);
         KAB_RTM_ADD(tm_tile, ta, tb);
-#ifdef KAB_BANDR_TIMING
-        long long cur_wait = 0;
-#endif
         // ---- ghost lanes: the lower neighbour's top 24 states after its group g-1 (message g-1)
         if (g > 0) {
 #ifdef KAB_BANDR_TIMING
@@ -639,11 +610,6 @@ __global__ void __launch_bounds__(KAB_BR_THREADS, 1)
 #endif
           if (need) {
             if (!owned) {
-              if (KAB_BR_LAG > 1 && !was_needed) {  // (re)joining the chain: let the warp below get KAB_BR_LAG groups ahead
-                const int mt = min(g - 1 + KAB_BR_LAG - 1, n_groups - 2);
-                const uint32_t ls = inbox + (uint32_t)(mt % MD) * (GH * 16u);
-                while (kab_lds_relaxed_b64(ls + 8).y != (uint32_t)(mt + 1)) __nanosleep(200);  // (a long wait: the
-              }                                                                   // chain is ~80 groups behind)
               const uint32_t slot = inbox + (uint32_t)((g - 1) % MD) * (GH * 16u);
               const uint32_t seq = (uint32_t)g;
               while (pf0.y != seq || pf1.y != seq) {
@@ -656,10 +622,8 @@ __global__ void __launch_bounds__(KAB_BR_THREADS, 1)
           } else if (!owned) {
             s0 = ninf; s1 = ninf;
           }
-          was_needed = need;
 #ifdef KAB_BANDR_TIMING
-          cur_wait = clock64() - tw0;
-          tm_wait += cur_wait; n_need += need;
+          tm_wait += clock64() - tw0; n_need += need;
 #endif
         }
         // message g (for the next group) may already be there: load it now, check it then
@@ -706,36 +670,24 @@ __global__ void __launch_bounds__(KAB_BR_THREADS, 1)
         // ---- backpointer word of this group -> staging; block finished?
         if (gib == 0 && blk >= KAB_BR_NBB)  // the buffer of block blk - NBB must have left shared memory
           while (bp_free < (uint32_t)(blk - KAB_BR_NBB + 1)) bp_free = kab_lds_relaxed_u32(ctrl + 4 * KAB_BR_C_BPFREE);
-        asm volatile("st.shared.u32 [%0], %1;" ::"r"(bpst + (uint32_t)((blk & (KAB_BR_NBB - 1)) * BG + gib) * 128u + (uint32_t)lane * 4u), "r"(bw) : "memory");
-        ++gib;
-        if (gib == BG || !more) {
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(bpst_lane + (uint32_t)(g & (KAB_BR_NBB * BG - 1)) * 128u), "r"(bw) : "memory");
+        if (gib == BG - 1 || !more) {
           kab_fence_proxy_async_smem();  // every lane's words -> visible to the bulk store
           kab_fence_cta();
           __syncwarp();
-          ++blk;
-          gib = 0;
-          if (lane == 0) kab_sts_relaxed_u32(ctrl + 4 * KAB_BR_C_BPREADY, (uint32_t)blk);
+          if (lane == 0) kab_sts_relaxed_u32(ctrl + 4 * KAB_BR_C_BPREADY, (uint32_t)(blk + 1));
         }
         KAB_RTM(tf);
         KAB_RTM_ADD(tm_bp, te, tf);
-#ifdef KAB_BANDR_TIMING
-        cat_t[need] += tf - ta; cat_n[need] += 1; cat_w[need] += cur_wait;
-        why_t[why] += tf - ta; why_n[why] += 1;
-#endif
       }
 #ifdef KAB_BANDR_TIMING
       if (lane == 0 && p.debug) {
         long long *d = p.debug + gw * 16;
         d[0] = tm_tile; d[1] = tm_msg; d[2] = tm_frames; d[3] = tm_pub; d[4] = tm_bp; d[5] = clock64() - tm_start;
-        d[6] = n_groups; d[7] = n_need; d[8] = tm_wait; d[9] = cat_t[0]; d[10] = cat_n[0]; d[11] = cat_w[0];
-        d[12] = cat_t[1]; d[13] = cat_n[1]; d[14] = cat_w[1];
+        d[6] = n_groups; d[7] = n_need; d[8] = tm_wait;
         p.debug[64 * 16 + 64 * 8 + gw * 2] = tm_fast; p.debug[64 * 16 + 64 * 8 + gw * 2 + 1] = n_fast;
-        if (gw < 8) printf("warp %2d (cw %d): common path %lld groups, %lld cycles each, of which waiting for the message %lld, tile wait %lld, frames %lld\n", gw, cw,
-               n_fast, n_fast ? tm_fast / n_fast : 0, n_fast ? (cat_w[0] + cat_w[1]) / n_fast : 0, n_fast ? tm_tile / n_fast : 0, n_fast ? tm_frames / n_fast : 0);
-        if (0) printf("warp %2d: general path: first %lld (%lld cyc), last %lld (%lld), mailbox room %lld (%lld each), bp buffer %lld (%lld each), rejoin %lld (%lld each)\n", gw,
-               why_n[0], why_t[0], why_n[1], why_t[1], why_n[2], why_n[2] ? why_t[2] / why_n[2] : 0, why_n[3], why_n[3] ? why_t[3] / why_n[3] : 0, why_n[4], why_n[4] ? why_t[4] / why_n[4] : 0);
-        if (0 && hd_n) printf("warp %2d: common-path groups without a message: %lld, %lld cycles each: tile wait %lld, message + loads %lld, frames %lld, rest %lld\n",
-                         gw, hd_n, hd_total / hd_n, hd_tile / hd_n, hd_pre / hd_n, hd_frames / hd_n, (hd_total - hd_tile - hd_pre - hd_frames) / hd_n);
+        if (gw < 4) printf("warp %2d (cw %d): common path %lld groups, %lld cycles each: tile wait + loads %lld, message poll %lld, frames %lld\n", gw, cw,
+               n_fast, n_fast ? tm_fast / n_fast : 0, n_fast ? tm_tile / n_fast : 0, n_fast ? tm_wait / n_fast : 0, n_fast ? tm_frames / n_fast : 0);
       }
 #endif
       // ---- end of the forward pass: cluster-wide forced end state (align.py:99-101)
