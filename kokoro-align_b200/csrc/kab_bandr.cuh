@@ -297,6 +297,7 @@ __global__ void __launch_bounds__(KAB_BR_THREADS, 1)
       long long pm_wait = 0, pm_tile = 0, pm_rest = 0, pm_safe = 0;
       const long long pm_start = clock64();
 #endif
+      uint32_t flags = 0;  // does the compute warp need its neighbour's message for the group being built?
       for (int c = 0; c < n_chunks; ++c) {
         const bool own = (c & 1) == pp;
         const uint32_t gc = ec0 + (uint32_t)c, st = gc % NS, ph = (gc / NS) & 1u;
@@ -332,7 +333,8 @@ __global__ void __launch_bounds__(KAB_BR_THREADS, 1)
           // does the compute warp need its neighbour's message for this group?  (same test as
           // kab_bandq.cuh: not if all 24 ghost states are outside the window for the whole group;
           // evaluated with the aliases of the previous group, before recycling)
-          uint32_t flags = 0;
+          const uint32_t flags_first = gi == 1 ? flags : 0u;  // (the chunk's first group)
+          flags = 0;
           if (own) {
             const int hi1g = min(lo1 + W, S);  // >= hi of every frame of this group
             const bool outside = owned || vb + 1 < lo_prev || vb >= hi1g;
@@ -381,7 +383,8 @@ __global__ void __launch_bounds__(KAB_BR_THREADS, 1)
           }
           if (!more) vbf[lane] = vb;  // final alias of this lane (the compute warp's forced end state)
           __syncwarp();  // (the tile's STS were issued before this warp's next STS: shared memory keeps a warp's stores in order)
-          if (lane == 0) kab_sts_relaxed_u32(ctrl + 4 * (KAB_BR_C_TILESEQ + t), (uint32_t)(g + 1) | (flags << 31));
+          // (the chunk's second word carries the first group's flag too: the compute warp reads one word per pair)
+          if (lane == 0) kab_sts_relaxed_u32(ctrl + 4 * (KAB_BR_C_TILESEQ + t), (uint32_t)(g + 1) | (flags << 31) | (flags_first << 30));
 #ifdef KAB_BANDR_TIMING
           pm_safe += safe;
 #endif
@@ -482,64 +485,87 @@ __global__ void __launch_bounds__(KAB_BR_THREADS, 1)
       const uint32_t f_pl = lane >= 32 - GH && !remote_up, f_pr = lane >= 32 - GH && remote_up;
       const int last_common = n_groups - 2;  // the groups 1 .. n_groups - 2 can take the common path
       int room_until = MD - 2;               // ... while the mailbox above is known to have room: g <= room_until
-      for (int g = 0; g < n_groups; ++g) {
-        // ---- COMMON PATH: every group but the first, the last and the rare wait for mailbox room.
-        // Straight-line code: a lone warp pays ~15 cycles per conditional block and 4-5 per dependent
-        // instruction, and in a chain that runs at its minimal lag EVERY group of every follower
-        // arrives just before its message, so the two polls (tile word, neighbour's message) are inline
-        // and the end-of-group stores are predicated.  A warp (re)joining the chain -- its ring slots
-        // recycled above the window -- comes through here too and simply waits for its first message:
-        // any start-up lag it were given is paid again at EVERY change of the head, i.e. every 18
-        // groups ((18 + lag) / 18 on the whole lattice; measured with a trace of group start times:
-        // two groups of intended lag plus the slow general body cost 6 groups per change, 8.4 -> 6.6 ms).
-        if ((unsigned)(g - 1) < (unsigned)min(last_common, room_until)) {
-          const uint32_t seq = (uint32_t)g;
+      // ghost lanes <- message g-1 (loaded a group ago, polled until it is there), then message g is
+      // loaded for the next group
+      auto take_message = [&](int g, bool need) {
+        const uint32_t seq = (uint32_t)g;
+        const uint32_t slot = inbox + (uint32_t)((g - 1) & (MD - 1)) * (GH * 16u);
+        while (!__all_sync(KAB_FULL_MASK, owned || !need || (pf0.y == seq && pf1.y == seq))) {
+          pf0 = kab_lds_relaxed_b64(slot);
+          pf1 = kab_lds_relaxed_b64(slot + 8);
+        }
+        if (!owned) {
+          s0 = need ? __uint_as_float(pf0.x) : ninf;
+          s1 = need ? __uint_as_float(pf1.x) : ninf;
+        }
+        const uint32_t nslot = inbox + (uint32_t)(g & (MD - 1)) * (GH * 16u);
+        pf0 = kab_lds_relaxed_b64(nslot);
+        pf1 = kab_lds_relaxed_b64(nslot + 8);
+      };
+      for (int g = 0; g < n_groups;) {
+        // ---- COMMON PATH: two groups (one emission chunk) per pass -- all of them but the first two,
+        // the last ones and the rare wait for mailbox room.  Straight-line code: a lone warp pays ~15
+        // cycles per conditional block and 4-5 per dependent instruction, and in a chain that runs at
+        // its minimal lag EVERY group of every follower arrives just before its message, so the polls
+        // (tile word once per pair, neighbour's message per group) are inline, the end-of-group stores
+        // are predicated, and the per-pass bookkeeping (loop test, tile word, progress counters, slot
+        // hand-back, block test) is paid once per 16 frames.  A warp (re)joining the chain -- its ring
+        // slots recycled above the window -- comes through here too and simply waits for its first
+        // message: any start-up lag it were given is paid again at EVERY change of the head, i.e.
+        // every 18 groups ((18 + lag) / 18 on the whole lattice; measured with a trace of group start
+        // times: two groups of intended lag plus the slow general body cost 6 groups per change,
+        // 8.4 -> 6.6 ms).  g is even here (the general body below takes two groups per pass).
+        if (g >= 2 && g + 1 <= min(last_common, room_until)) {
           const int t = g & (TD - 1);
           KAB_RTM(fa);
-#ifndef KAB_BR_EXP_NOTILEWAIT
-          while ((tw & 0x7fffffffu) != seq + 1u) tw = kab_lds_relaxed_u32(ctrl + 4 * (KAB_BR_C_TILESEQ + t));
-#endif
+          // the chunk's second tile word (published last) carries both need flags
+          while ((tw & 0x3fffffffu) != (uint32_t)g + 2u) tw = kab_lds_relaxed_u32(ctrl + 4 * (KAB_BR_C_TILESEQ + t + 1));
 #ifdef KAB_BR_EXP_NOMSG
-          const bool need = false;
+          const bool need0 = false, need1 = false;
 #else
-          const bool need = (tw >> 31) != 0u;
+          const bool need0 = (tw & 0x40000000u) != 0u, need1 = (tw >> 31) != 0u;
 #endif
           const uint32_t tl = tiles_lane + (uint32_t)t * 2048u;
-          float2 e[G];
+          float2 e[G], e2[G];
 #pragma unroll
           for (int f = 0; f < G; ++f)
             asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(e[f].x), "=f"(e[f].y) : "r"(tl + f * 256) : "memory");
-          tw = kab_lds_relaxed_u32(ctrl + 4 * (KAB_BR_C_TILESEQ + ((t + 1) & (TD - 1))));
-          const uint32_t up_done_now = read_up_done();  // (used after the frames: mailbox room without a wait)
           KAB_RTM(fw0);
-          {  // ghost lanes: the lower neighbour's top 24 states (message g-1, loaded a group ago)
-            const uint32_t slot = inbox + (uint32_t)((g - 1) & (MD - 1)) * (GH * 16u);
-            while (!__all_sync(KAB_FULL_MASK, owned || !need || (pf0.y == seq && pf1.y == seq))) {
-              pf0 = kab_lds_relaxed_b64(slot);
-              pf1 = kab_lds_relaxed_b64(slot + 8);
-            }
-          }
+          take_message(g, need0);
           KAB_RTM(fw1);
-          if (!owned) {
-            s0 = need ? __uint_as_float(pf0.x) : ninf;
-            s1 = need ? __uint_as_float(pf1.x) : ninf;
-          }
-          {
-            const uint32_t slot = inbox + (uint32_t)(g & (MD - 1)) * (GH * 16u);
-            pf0 = kab_lds_relaxed_b64(slot);
-            pf1 = kab_lds_relaxed_b64(slot + 8);
-          }
+#pragma unroll
+          for (int f = 0; f < G; ++f)
+            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(e2[f].x), "=f"(e2[f].y) : "r"(tl + 2048 + f * 256) : "memory");
+          tw = kab_lds_relaxed_u32(ctrl + 4 * (KAB_BR_C_TILESEQ + ((t + 3) & (TD - 1))));  // next pair's
+          const uint32_t up_done_now = read_up_done();  // (used after the frames: mailbox room without a wait)
           bw = 0;
           KAB_RTM(ff0);
-#ifdef KAB_BR_EXP_NOFRAMES
-          s0 += e[0].x + e[7].y; s1 += e[3].x;
-#else
 #pragma unroll
           for (int f = 0; f < G; ++f) frame(e[f].x, e[f].y, 4 * f);
-#endif
           KAB_RTM(ff1);
-          // message g first (the warp above is waiting for it), then: group g is finished, its tile
-          // has been read (the prep warps may reuse the slot), progress for the warp below
+          // message g at once: the warp above is waiting for it
+          asm volatile(
+              "{\n\t.reg .pred p2, p3;\n\t.reg .b64 q0, q1;\n\t"
+              "setp.ne.u32 p2, %0, 0;\n\t"
+              "setp.ne.u32 p3, %1, 0;\n\t"
+              "mov.b64 q0, {%4, %3};\n\t"
+              "mov.b64 q1, {%5, %3};\n\t"
+              "@p2 st.shared.v2.b32 [%2], {%4, %3};\n\t"
+              "@p2 st.shared.v2.b32 [%2+8], {%5, %3};\n\t"
+              "@p3 st.relaxed.cluster.shared::cluster.b64 [%2], q0;\n\t"
+              "@p3 st.relaxed.cluster.shared::cluster.b64 [%2+8], q1;\n\t}" ::"r"(f_pl),
+              "r"(f_pr), "r"(up_mbox + (uint32_t)(g & (MD - 1)) * (GH * 16u)), "r"((uint32_t)g + 1u), "r"(__float_as_uint(s0)), "r"(__float_as_uint(s1))
+              : "memory");
+          const uint32_t bw0 = bw;
+          KAB_RTM(fx0);
+          take_message(g + 1, need1);
+          KAB_RTM(fx1);
+          bw = 0;
+#pragma unroll
+          for (int f = 0; f < G; ++f) frame(e2[f].x, e2[f].y, 4 * f);
+          KAB_RTM(fx2);
+          // message g + 1, then: both groups are finished, their tiles have been read (the prep warps
+          // may reuse the slots), progress for the warp below
           asm volatile(
               "{\n\t.reg .pred p0, p1, p2, p3;\n\t.reg .b64 q0, q1;\n\t"
               "setp.ne.u32 p2, %2, 0;\n\t"
@@ -554,14 +580,18 @@ __global__ void __launch_bounds__(KAB_BR_THREADS, 1)
               "@p3 st.relaxed.cluster.shared::cluster.b64 [%8+8], q1;\n\t"
               "@p0 st.relaxed.cluster.shared::cta.u32 [%4], %5;\n\t"
               "@p0 mbarrier.arrive.shared::cta.b64 _, [%6];\n\t"
+              "@p0 mbarrier.arrive.shared::cta.b64 _, [%6+8];\n\t"
               "@p1 st.shared::cluster.u32 [%7], %5;\n\t}" ::"r"(f_l0),
-              "r"(f_dn), "r"(f_pl), "r"(f_pr), "r"(ctrl + 4 * KAB_BR_C_COMPDONE), "r"(seq + 1u), "r"(slotfree_u32 + (uint32_t)t * 8u),
-              "r"(down_done), "r"(up_mbox + (uint32_t)(g & (MD - 1)) * (GH * 16u)), "r"(__float_as_uint(s0)), "r"(__float_as_uint(s1))
+              "r"(f_dn), "r"(f_pl), "r"(f_pr), "r"(ctrl + 4 * KAB_BR_C_COMPDONE), "r"((uint32_t)g + 2u), "r"(slotfree_u32 + (uint32_t)t * 8u),
+              "r"(down_done), "r"(up_mbox + (uint32_t)((g + 1) & (MD - 1)) * (GH * 16u)), "r"(__float_as_uint(s0)), "r"(__float_as_uint(s1))
               : "memory");
-          asm volatile("st.shared.u32 [%0], %1;" ::"r"(bpst_lane + (uint32_t)(g & (KAB_BR_NBB * BG - 1)) * 128u), "r"(bw) : "memory");
+          {
+            const uint32_t ba = bpst_lane + (uint32_t)(g & (KAB_BR_NBB * BG - 1)) * 128u;
+            asm volatile("st.shared.u32 [%0], %1;\n\tst.shared.u32 [%0+128], %2;" ::"r"(ba), "r"(bw0), "r"(bw) : "memory");
+          }
           up_done_seen = max(up_done_seen, up_done_now);
           room_until = (int)up_done_seen + MD - 2;
-          if ((g & (BG - 1)) == BG - 1) {  // the block is complete: hand it to the prep warp's bulk store
+          if ((g & (BG - 1)) == BG - 2) {  // the block is complete: hand it to the prep warp's bulk store
             kab_fence_proxy_async_smem();
             kab_fence_cta();
             __syncwarp();
@@ -574,10 +604,14 @@ __global__ void __launch_bounds__(KAB_BR_THREADS, 1)
               while (bp_free < (uint32_t)(blk - KAB_BR_NBB + 1)) bp_free = kab_lds_relaxed_u32(ctrl + 4 * KAB_BR_C_BPFREE);
           }
 #ifdef KAB_BANDR_TIMING
-          { const long long fb = clock64(); tm_fast += fb - fa; ++n_fast; n_need += need; tm_wait += fw1 - fw0; tm_frames += ff1 - ff0; tm_tile += fw0 - fa; }
+          { const long long fb = clock64(); tm_fast += fb - fa; n_fast += 2; n_need += need0 + need1; tm_wait += fw1 - fw0 + fx1 - fx0;
+            tm_frames += ff1 - ff0 + fx2 - fx1; tm_tile += fw0 - fa; }
 #endif
+          g += 2;
           continue;
         }
+        // ---- GENERAL BODY: one group, every wait spelled out; two per pass so that g stays even
+        for (int rep = 0; rep < 2 && g < n_groups; ++rep, ++g) {
         const int gib = g & (BG - 1), blk = g / BG;  // group inside its backpointer block, block index
         const int i0 = g * G, nfr = min(G, T - i0);
         const bool more = i0 + G < T;
@@ -592,7 +626,7 @@ __global__ void __launch_bounds__(KAB_BR_THREADS, 1)
         }
 #endif
         // ---- this group's tile (its word was loaded during the previous group)
-        while ((tw & 0x7fffffffu) != (uint32_t)(g + 1)) tw = kab_lds_relaxed_u32(ctrl + 4 * (KAB_BR_C_TILESEQ + t));
+        while ((tw & 0x3fffffffu) != (uint32_t)(g + 1)) tw = kab_lds_relaxed_u32(ctrl + 4 * (KAB_BR_C_TILESEQ + t));
         const bool need = (tw >> 31) != 0u;
         const float2 *tile = reinterpret_cast<const float2 *>(kab_smem + geo.tile_off + (size_t)cw * (TD * 2048) + (size_t)t * 2048) + lane;
         float2 e[G];
@@ -679,6 +713,7 @@ __global__ void __launch_bounds__(KAB_BR_THREADS, 1)
         }
         KAB_RTM(tf);
         KAB_RTM_ADD(tm_bp, te, tf);
+        }
       }
 #ifdef KAB_BANDR_TIMING
       if (lane == 0 && p.debug) {
