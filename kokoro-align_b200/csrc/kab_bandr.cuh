@@ -30,6 +30,9 @@
 #include "kab_common.cuh"
 
 #ifndef KAB_BR_CW
+#ifndef KAB_BR_EXP_FRAMES
+#define KAB_BR_EXP_FRAMES 8
+#endif
 #define KAB_BR_CW 4           // compute warps per CTA (and as many prep warps): ONE compute warp per scheduler.  The
                               // SM sub-partition issues ~1 instruction per cycle and a warp at most every other
                               // cycle; with two compute + two prep warps per scheduler the compute warps got a
@@ -502,6 +505,9 @@ __global__ void __launch_bounds__(KAB_BR_THREADS, 1)
         pf0 = kab_lds_relaxed_b64(nslot);
         pf1 = kab_lds_relaxed_b64(nslot + 8);
       };
+#ifdef KAB_BANDR_TOTAL
+      const long long tot0 = clock64();
+#endif
       for (int g = 0; g < n_groups;) {
         // ---- COMMON PATH: two groups (one emission chunk) per pass -- all of them but the first two,
         // the last ones and the rare wait for mailbox room.  Straight-line code: a lone warp pays ~15
@@ -541,7 +547,7 @@ __global__ void __launch_bounds__(KAB_BR_THREADS, 1)
           bw = 0;
           KAB_RTM(ff0);
 #pragma unroll
-          for (int f = 0; f < G; ++f) frame(e[f].x, e[f].y, 4 * f);
+          for (int f = 0; f < KAB_BR_EXP_FRAMES; ++f) frame(e[f].x, e[f].y, 4 * f);
           KAB_RTM(ff1);
           // message g at once: the warp above is waiting for it
           asm volatile(
@@ -562,7 +568,7 @@ __global__ void __launch_bounds__(KAB_BR_THREADS, 1)
           KAB_RTM(fx1);
           bw = 0;
 #pragma unroll
-          for (int f = 0; f < G; ++f) frame(e2[f].x, e2[f].y, 4 * f);
+          for (int f = 0; f < KAB_BR_EXP_FRAMES; ++f) frame(e2[f].x, e2[f].y, 4 * f);
           KAB_RTM(fx2);
           // message g + 1, then: both groups are finished, their tiles have been read (the prep warps
           // may reuse the slots), progress for the warp below
@@ -715,6 +721,9 @@ __global__ void __launch_bounds__(KAB_BR_THREADS, 1)
         KAB_RTM_ADD(tm_bp, te, tf);
         }
       }
+#ifdef KAB_BANDR_TOTAL
+      if (lane == 0 && (gw & 3) == 0) printf("warp %2d: %lld cycles per group (compute loop, %d groups)\n", gw, (clock64() - tot0) / n_groups, n_groups);
+#endif
 #ifdef KAB_BANDR_TIMING
       if (lane == 0 && p.debug) {
         long long *d = p.debug + gw * 16;
