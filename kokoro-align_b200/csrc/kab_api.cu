@@ -466,7 +466,7 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
     // Its clusters take lattices from the work queue, so a plan may hold more lattices than clusters.
     // KAB_BAND_R=0 disables it, =1 forces it whenever its geometry allows.
     const int ncr = (nwq + KAB_BR_CW - 1) / KAB_BR_CW;
-    const bool r_ok = ncr <= 8 && pl->stage_frames == KAB_BR_F && kab_bandr_geom(pl->stage_bytes).smem_bytes <= 227 * 1024;
+    const bool r_ok = ncr <= 16 && pl->stage_frames == KAB_BR_F && kab_bandr_geom(pl->stage_bytes).smem_bytes <= 227 * 1024;
     const char *qe = getenv("KAB_BAND_Q");
     const int want_q = qe ? atoi(qe) : -1;
     const char *re = getenv("KAB_BAND_R");
@@ -620,6 +620,9 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
       const int threads = pl->band_r ? KAB_BR_THREADS : (pl->band_q ? KAB_BQ_THREADS : KAB_BP_THREADS);
       if ((e = ensure_dyn_smem(fn, device, smem_b)) != cudaSuccess) { rc = cuda_fail(e, "cudaFuncSetAttribute(cluster band)"); break; }
       pl->smem[Q_BAND] = smem_b;
+      if (pl->band_nc > 8 && (e = cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)) != cudaSuccess) {
+        rc = cuda_fail(e, "cudaFuncSetAttribute(non-portable cluster size)"); break;
+      }
       cudaLaunchConfig_t cfg{};
       cudaLaunchAttribute at[1];
       at[0].id = cudaLaunchAttributeClusterDimension;

@@ -29,10 +29,10 @@
 #include "kab_bandq.cuh"
 #include "kab_common.cuh"
 
-#ifndef KAB_BR_CW
 #ifndef KAB_BR_EXP_FRAMES
-#define KAB_BR_EXP_FRAMES 8
+#define KAB_BR_EXP_FRAMES 8   // what-if builds only: frames executed per group (results are wrong below 8)
 #endif
+#ifndef KAB_BR_CW
 #define KAB_BR_CW 4           // compute warps per CTA (and as many prep warps): ONE compute warp per scheduler.  The
                               // SM sub-partition issues ~1 instruction per cycle and a warp at most every other
                               // cycle; with two compute + two prep warps per scheduler the compute warps got a
@@ -48,7 +48,11 @@
 #define KAB_BR_MD 16          // mailbox depth (messages)
 #define KAB_BR_BG 16          // groups per backpointer block (2 KB)
 #define KAB_BR_NBB 4          // backpointer staging buffers per compute warp
+#ifdef KAB_BR_ISOLATE          // experiment: 2 compute warps alone on schedulers 0 and 1, the helpers on 2 and 3
+#define KAB_BR_THREADS (12 * 32)
+#else
 #define KAB_BR_THREADS ((3 * KAB_BR_CW + 1) * 32)
+#endif
 
 struct KabBandrGeom {
   size_t ctrl_off, tile_off, mbox_off, bp_off, vbf_off, wtab_off, stage_off, smem_bytes;
@@ -155,10 +159,20 @@ __global__ void __launch_bounds__(KAB_BR_THREADS, 1)
   const bool is_prod = vw == 0, is_prep = vw >= 1 && vw <= 2 * CW;
   const int pp = is_prep ? (vw - 1) & 1 : 0;
   const int cw = is_prep ? (vw - 1) >> 1 : (vw > 2 * CW ? vw - 1 - 2 * CW : 0);
+#elif defined(KAB_BR_ISOLATE)
+  static_assert(CW == 2, "isolated layout: two compute warps");
+  // ids 8, 9 compute (schedulers 0, 1, alone); 2, 3 / 6, 7 prep; 10 producer; 0, 1, 4, 5, 11 idle at the barriers
+  const bool is_prod = warp == 10, is_prep = warp == 2 || warp == 3 || warp == 6 || warp == 7;
+  const bool is_idle = warp == 0 || warp == 1 || warp == 4 || warp == 5 || warp == 11;
+  const int pp = is_prep ? (warp >> 2) : 0;
+  const int cw = is_prep ? (warp & 1) : (warp == 9 ? 1 : 0);
 #else
   const bool is_prod = warp == 0, is_prep = warp >= 1 && warp <= 2 * CW;
   const int pp = is_prep ? (warp - 1) & 1 : 0;                                        // parity a prep warp builds
   const int cw = is_prep ? (warp - 1) >> 1 : (warp > 2 * CW ? warp - 1 - 2 * CW : 0);  // the compute warp this warp is / serves
+#endif
+#ifndef KAB_BR_ISOLATE
+  constexpr bool is_idle = false;
 #endif
   const int gw = (int)rank * CW + cw;         // its global index in the ring
   const bool owned = lane >= GH;
@@ -412,7 +426,7 @@ __global__ void __launch_bounds__(KAB_BR_THREADS, 1)
         while (bp_issued < n_blocks) service_bp();
         if (lane == 0) kab_bulk_wait0();  // the compute warp's backpointer blocks are in global memory
       }
-    } else {
+    } else if (!is_idle) {
       // ================= compute warp: the recurrence
       // Nothing here waits on a fence: every hand-over is a word that carries its own sequence
       // number, polled in shared memory (the LSU of an SM executes a warp's shared-memory accesses in
@@ -425,10 +439,14 @@ __global__ void __launch_bounds__(KAB_BR_THREADS, 1)
         const float h2 = __shfl_up_sync(KAB_FULL_MASK, s0, 1);  // state vb - 2
         const float h3 = __shfl_up_sync(KAB_FULL_MASK, s1, 2);  // state vb - 3
         float t0, th1, a0, a1, a2, a3;
-        kab_add2(s0, h1, xb, t0, th1);        // blank <- vb (move 0), vb - 1 (move 1)
+        // two register pairs feed the three packed adds: (vb, vb - 1) gets both emissions, (vb + 1, vb - 2)
+        // the label's -- with the pairs (vb, vb - 1), (vb, vb + 1), (vb - 2, vb - 1) ptxas needed three
+        // copies per frame, and a lone warp's frame is issue bound (one instruction every other cycle)
+        const unsigned long long pu = kab_pack2(s0, h1), pv = kab_pack2(s1, h2);
+        kab_add2p(pu, xb, t0, th1);           // blank <- vb (move 0), vb - 1 (move 1)
         const float th3 = __fadd_rn(h3, xb);  // vb - 3 (move 3)
-        kab_add2(s0, s1, x1, a1, a0);         // label <- vb + 1 (move 0), vb (move 1)
-        kab_add2(h2, h1, x1, a3, a2);         //       <- vb - 1 (move 2), vb - 2 (move 3)
+        kab_add2p(pu, x1, a1, a2);            // label <- vb (move 1), vb - 1 (move 2)
+        kab_add2p(pv, x1, a0, a3);            //       <- vb + 1 (move 0), vb - 2 (move 3)
         const float m0 = kab_blank_sel(t0, kab_mm<MM>(th1, p.mm1), kab_mm<MM>(th3, p.mm3), bw, 1u << (sh + 0), 2u << (sh + 0), one);
         const float m1 = kab_label_sel(a0, kab_mm<MM>(a1, p.mm1), kab_mm<MM>(a2, p.mm2), kab_mm<MM>(a3, p.mm3), bw, 1u << (sh + 2), 2u << (sh + 2), one);
         s0 = m0; s1 = m1;
@@ -611,7 +629,13 @@ __global__ void __launch_bounds__(KAB_BR_THREADS, 1)
           }
 #ifdef KAB_BANDR_TIMING
           { const long long fb = clock64(); tm_fast += fb - fa; n_fast += 2; n_need += need0 + need1; tm_wait += fw1 - fw0 + fx1 - fx0;
-            tm_frames += ff1 - ff0 + fx2 - fx1; tm_tile += fw0 - fa; }
+            tm_frames += ff1 - ff0 + fx2 - fx1; tm_tile += fw0 - fa;
+            if (lane == 0 && p.debug && g < 16384) {  // per-pass trace: start (SM clock), tile wait, both message waits, frames, flags
+              long long *d = p.debug + 64 * 26 + ((size_t)gw * 16384 + g) * 2;
+              d[0] = fa;
+              d[1] = (fw0 - fa) | ((fw1 - fw0) << 12) | ((fx1 - fx0) << 24) | ((ff1 - ff0 + fx2 - fx1) << 36) | ((long long)need0 << 50) | ((long long)need1 << 51);
+              d[2] = fb; d[3] = 0;
+            } }
 #endif
           g += 2;
           continue;
@@ -705,6 +729,11 @@ __global__ void __launch_bounds__(KAB_BR_THREADS, 1)
           }
           if (lane >= 32 - GH) publish(up_mbox + (uint32_t)(g % MD) * (GH * 16u), (uint32_t)(g + 1));
         }
+        // (the common path's room test reads room_until: without this refresh a warp that once ran
+        // into the limit -- every warp does, free-running while its ring slots are outside the window --
+        // stayed in this body for the rest of the lattice: 68 % of all groups, found in the ncu source page)
+        up_done_seen = max(up_done_seen, read_up_done());
+        room_until = (int)up_done_seen + MD - 2;
         KAB_RTM(te);
         KAB_RTM_ADD(tm_pub, td, te);
         // ---- backpointer word of this group -> staging; block finished?
@@ -752,7 +781,7 @@ __global__ void __launch_bounds__(KAB_BR_THREADS, 1)
 
     const int v = *s_vmax;
     const int status = *s_bad ? 3 : (v < 0 ? 1 : 0);
-    if (!is_prod && !is_prep && owned && status == 0 && p.final_score) {  // (compute warps)
+    if (!is_prod && !is_prep && !is_idle && owned && status == 0 && p.final_score) {  // (compute warps)
       if (vb + 0 == v) p.final_score[lat.index] = s0;
       if (vb + 1 == v) p.final_score[lat.index] = s1;
     }

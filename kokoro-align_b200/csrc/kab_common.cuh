@@ -167,6 +167,23 @@ __device__ __forceinline__ void kab_add2(float lo, float hi, float e, float &olo
       : "=f"(olo), "=f"(ohi)
       : "f"(lo), "f"(hi), "f"(e));
 }
+// The same with the pair already packed (one register pair feeding two packed adds needs no copies):
+// kab_pack2(lo, hi) once, kab_add2p(pair, e, ...) per addend.
+__device__ __forceinline__ unsigned long long kab_pack2(float lo, float hi) {
+  unsigned long long u;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(u) : "f"(lo), "f"(hi));
+  return u;
+}
+__device__ __forceinline__ void kab_add2p(unsigned long long u, float e, float &olo, float &ohi) {
+  asm("{\n\t"
+      ".reg .b64 v, w;\n\t"
+      "mov.b64 v, {%3, %3};\n\t"
+      "add.rn.f32x2 w, %2, v;\n\t"
+      "mov.b64 {%0, %1}, w;\n\t"
+      "}"
+      : "=f"(olo), "=f"(ohi)
+      : "l"(u), "f"(e));
+}
 // Packed add with two different addends: olo = lo + elo, ohi = hi + ehi (two IEEE-rn fp32 adds).
 __device__ __forceinline__ void kab_add2v(float lo, float hi, float elo, float ehi, float &olo, float &ohi) {
   asm("{\n\t"

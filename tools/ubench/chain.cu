@@ -111,7 +111,7 @@ void run(const char *name, int per_iter, int warps, int active) {
 // slot: NOISE 0 = helpers exit, 1 = tight LDS poll, 2 = poll + __nanosleep(100), 3 = poll + __nanosleep(1000),
 // 4 = helpers build tiles continuously (16 LDS + 8 STS.64 per iteration)
 template <int NOISE>
-__global__ void kn(float *out, long long *cyc, float e, volatile int *flag) {
+__global__ void kn(float *out, long long *cyc, float e, volatile int *flag, int ninf_lanes = 0) {
   __shared__ int word;
   __shared__ __align__(16) float buf[4096];
   const int warp = threadIdx.x >> 5;
@@ -122,6 +122,9 @@ __global__ void kn(float *out, long long *cyc, float e, volatile int *flag) {
     float s0 = threadIdx.x * 0.001f, s1 = s0 + 1.f;
     uint32_t bw = 0, acc = 0;
     const uint32_t one = e > 0 ? 1u : 0u;
+    // lanes below ninf_lanes: states outside the window (scores and masked emissions -inf), as at the
+    // band's edges and in a warp whose ring slots are outside the window
+    if ((int)(threadIdx.x & 31) < ninf_lanes) { s0 = s1 = e = -__int_as_float(0x7f800000); }
     const long long c0 = clock64();
 #pragma unroll 8
     for (int i = 0; i < N; ++i) {
@@ -163,12 +166,12 @@ __global__ void kn(float *out, long long *cyc, float e, volatile int *flag) {
   }
 }
 template <int NOISE>
-void runn(const char *name) {
+void runn(const char *name, int ninf_lanes = 0) {
   float *out; long long *cyc; int *flag;
   cudaMalloc(&out, 4096 * 4); cudaMalloc(&cyc, 64 * 8); cudaMalloc(&flag, 4);
-  kn<NOISE><<<1, 12 * 32>>>(out, cyc, 0.5f, flag);
+  kn<NOISE><<<1, 12 * 32>>>(out, cyc, 0.5f, flag, ninf_lanes);
   cudaDeviceSynchronize();
-  kn<NOISE><<<1, 12 * 32>>>(out, cyc, 0.5f, flag);
+  kn<NOISE><<<1, 12 * 32>>>(out, cyc, 0.5f, flag, ninf_lanes);
   cudaDeviceSynchronize();
   long long h[4];
   cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
@@ -178,6 +181,10 @@ void runn(const char *name) {
 
 int main() {
   runn<0>("exit at once");
+  runn<0>("exit at once, 1 lane at -inf", 1);
+  runn<0>("exit at once, 12 lanes at -inf", 12);
+  runn<0>("exit at once, all lanes at -inf", 32);
+  runn<4>("build tiles, 12 lanes at -inf", 12);
   runn<1>("tight shared-memory poll");
   runn<2>("poll + __nanosleep(100)");
   runn<3>("poll + __nanosleep(1000)");
