@@ -539,7 +539,7 @@ __global__ void __launch_bounds__(KAB_BR_THREADS, 1)
         // every 18 groups ((18 + lag) / 18 on the whole lattice; measured with a trace of group start
         // times: two groups of intended lag plus the slow general body cost 6 groups per change,
         // 8.4 -> 6.6 ms).  g is even here (the general body below takes two groups per pass).
-        if (g >= 2 && g + 1 <= min(last_common, room_until)) {
+        while (g >= 2 && g + 1 <= min(last_common, room_until)) {  // (its own compact loop: one backward branch)
           const int t = g & (TD - 1);
           KAB_RTM(fa);
           // the chunk's second tile word (published last) carries both need flags
@@ -638,8 +638,8 @@ __global__ void __launch_bounds__(KAB_BR_THREADS, 1)
             } }
 #endif
           g += 2;
-          continue;
         }
+        if (g >= n_groups) break;
         // ---- GENERAL BODY: one group, every wait spelled out; two per pass so that g stays even
         for (int rep = 0; rep < 2 && g < n_groups; ++rep, ++g) {
         const int gib = g & (BG - 1), blk = g / BG;  // group inside its backpointer block, block index
