@@ -141,6 +141,8 @@ struct kab_plan {
   int32_t band_nc = 0;  // > 0: a cluster band kernel (kab_bandp.cuh / kab_bandq.cuh) with clusters of band_nc CTAs
   bool band_q = false;  // the cluster kernel is kab_bandq_kernel / kab_bandr_kernel (two states per lane, KabBtLayoutQ)
   bool band_r = false;  // ... kab_bandr_kernel (warp-specialised: prep warps, shared-memory mailboxes)
+  bool band_ga = false;  // the band lattices run kab_bandr_kernel in its gather mode (V > 512: emissions straight from the
+                         // caller's log-probs, any number of distinct labels, no compact copy)
   int32_t band_cw = 0;  // compute warps per CTA of that kernel (ring of 40 * band_cw * band_nc slots)
   kab_plan_info info{};
   std::vector<KabLattice> lists[N_QUEUES];
@@ -310,6 +312,25 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
   // ---- wide vocabularies: can the staged kernels work on a compact copy of the log-probs?
   // (every lattice they would take uses at most MAX_STAGE_V - 1 distinct label columns)
   std::vector<int32_t> h_gather;
+  // Band-shaped lattices of a wide vocabulary do not need the compact copy at all: kab_bandr.cuh's
+  // gather mode reads log_probs[t, label] itself (a chapter with more than
+  // 511 distinct BPE tokens sent the whole plan to the generic kernel).  It is used when every
+  // band-shaped lattice of the plan fits that kernel's ring (beam + 32 <= 1280 states).
+  const int64_t ga_max_weff = (int64_t)KAB_BQ_OW * KAB_BR_CW * 8 - 32;
+  auto band_shaped = [&](int64_t T, int64_t S) {
+    const bool full = W >= S && T > 0 && (S * (T - 1)) / T <= W / 2;
+    if (full && S <= 248) return false;  // warp class
+    return W >= 1 && S <= 3 * T && std::min<int64_t>(W, S) + 32 <= (int64_t)KAB_BAND_OW * BAND_MAX_WARPS;
+  };
+  {
+    const char *ge = getenv("KAB_BAND_GATHER");
+    bool ok = V > MAX_STAGE_V && M <= 4 && !(ge && atoi(ge) == 0) && kab_bandr_geom(64).smem_bytes <= 227 * 1024, any_band = false;
+    for (int64_t b = 0; b < B && ok; ++b) {
+      const int64_t T = t_off[b + 1] - t_off[b], S = 2 * (l_off[b + 1] - l_off[b]) + 1;
+      if (band_shaped(T, S)) { any_band = true; ok = std::min<int64_t>(W, S) <= ga_max_weff; }
+    }
+    pl->band_ga = ok && any_band;
+  }
   if (V > MAX_STAGE_V && M <= 4) {
     std::vector<uint8_t> seen((size_t)V, 0);
     int64_t dmax = 0;
@@ -317,6 +338,7 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
     for (int64_t b = 0; b < B; ++b) {
       const int64_t L = l_off[b + 1] - l_off[b];
       const int32_t *lab = labels + l_off[b];
+      if (pl->band_ga && band_shaped(t_off[b + 1] - t_off[b], 2 * L + 1)) continue;  // (not through the compact copy)
       bool usable = true;
       int64_t dist = 0;
       for (int64_t l = 0; l < L && usable; ++l) {
@@ -387,7 +409,8 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
     d.lab_off = l_off[b];
     d.T = (int32_t)T; d.L = (int32_t)L; d.index = (int32_t)b;
     d.col_off = (int64_t)col16.size();
-    if (pl->Vc && !special) {
+    const bool ga = pl->band_ga && !special && band_shaped(T, S);  // gather mode: the labels stay column numbers
+    if (pl->Vc && !special && !ga && distinct + 1 <= pl->Vc) {
       // compact numbering: blank 0, then the lattice's distinct label columns in ascending order
       int32_t *g = h_gather.data() + (size_t)b * pl->Vc;
       int32_t n = 1;
@@ -403,11 +426,11 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
 
     // max_move 1 .. 3 run in the same kernels (their MM instantiations turn the excluded moves'
     // candidates into -inf); more than four moves only exist in the generic kernel
-    const bool fast = M <= 4 && !special && Veff <= MAX_STAGE_V;
+    const bool fast = M <= 4 && !special && (ga || (Veff <= MAX_STAGE_V && (!pl->Vc || distinct + 1 <= pl->Vc)));
     const bool full = W >= S && (S * (T - 1)) / T <= W / 2;
     const int64_t weff = std::min<int64_t>(W, S);
     int q;
-    if (fast && full && S <= 248) {
+    if (fast && !ga && full && S <= 248) {
       q = Q_WARP;
       d.k = S <= 62 ? 2 : (S <= 124 ? 4 : (S <= 186 ? 6 : 8));  // 31 lanes x K states
       const int fpw = d.k <= 2 ? 8 : (d.k <= 4 ? 4 : 2);
@@ -416,7 +439,7 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
     } else if (fast && W >= 1 && S <= 3 * T && weff + 32 <= KAB_BAND_OW * BAND_MAX_WARPS) {
       q = Q_BAND;  // backpointer offsets are assigned below, once the ring size is known
       max_band_weff = std::max(max_band_weff, weff);
-    } else if (fast && M == 4 && full && ((S + KAB_BAND_OW - 1) / KAB_BAND_OW + KAB_WD_CW - 1) / KAB_WD_CW + 1 <= wide_capacity) {
+    } else if (fast && !ga && M == 4 && full && ((S + KAB_BAND_OW - 1) / KAB_BAND_OW + KAB_WD_CW - 1) / KAB_WD_CW + 1 <= wide_capacity) {
       q = Q_WIDE;  // unbanded and wider than a CTA: a chain of warps over the whole GPU
       const int nww = (int)((S + KAB_BAND_OW - 1) / KAB_BAND_OW);
       d.k = nww;
@@ -466,7 +489,7 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
     // Its clusters take lattices from the work queue, so a plan may hold more lattices than clusters.
     // KAB_BAND_R=0 disables it, =1 forces it whenever its geometry allows.
     const int ncr = (nwq + KAB_BR_CW - 1) / KAB_BR_CW;
-    const bool r_ok = ncr <= 16 && pl->stage_frames == KAB_BR_F && kab_bandr_geom(pl->stage_bytes).smem_bytes <= 227 * 1024;
+    const bool r_ok = pl->band_ga || (ncr <= 8 && pl->stage_frames == KAB_BR_F && kab_bandr_geom(pl->stage_bytes).smem_bytes <= 227 * 1024);
     const char *qe = getenv("KAB_BAND_Q");
     const int want_q = qe ? atoi(qe) : -1;
     const char *re = getenv("KAB_BAND_R");
@@ -480,7 +503,7 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
     for (const KabLattice &d : pl->lists[Q_BAND]) { sum_t += d.T; max_t = std::max(max_t, (double)d.T); }
     const double est_r = std::max(max_t, sum_t / std::max(1, pl->sm_count / std::max(1, ncr))) * 108.0;
     const double est_b = std::max(max_t, sum_t / (double)(pl->sm_count * (pl->band_nw <= 16 ? 2 : 1))) * 190.0;
-    const bool use_r = r_ok && want_r != 0 && want_nc != 0 && want_q != 0 && (want_r >= 1 || want_nc >= 1 || est_r <= est_b);
+    const bool use_r = pl->band_ga || (r_ok && want_r != 0 && want_nc != 0 && want_q != 0 && (want_r >= 1 || want_nc >= 1 || est_r <= est_b));
     const bool use_q = !use_r && M == 4 && q_ok && want_q != 0 && want_nc != 0 && (want_q >= 1 || n_band <= pl->sm_count / ncq);
     if (use_r || use_q) {
       pl->band_q = true;
@@ -613,16 +636,14 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
     }
     if (!pl->lists[Q_BAND].empty() && pl->band_nc > 0) {
       if ((e = pool_malloc((void **)&pl->d_band_fifo, (size_t)pl->band_fifo_bytes)) != cudaSuccess) { rc = cuda_fail(e, "pool_malloc(band FIFOs)"); break; }
-      const size_t smem_b = pl->band_r ? kab_bandr_geom(pl->stage_bytes).smem_bytes
+      const size_t smem_b = pl->band_r ? kab_bandr_geom(pl->band_ga ? 64 : pl->stage_bytes).smem_bytes
                                        : (pl->band_q ? kab_bandq_geom(pl->stage_bytes).smem_bytes : kab_bandp_geom(pl->stage_bytes).smem_bytes);
-      const void *fn = pl->band_r ? (M == 4 ? (const void *)kab_bandr_kernel<false> : (const void *)kab_bandr_kernel<true>)
+      const void *fn = pl->band_r ? (pl->band_ga ? (M == 4 ? (const void *)kab_bandr_kernel<false, true> : (const void *)kab_bandr_kernel<true, true>)
+                                                 : (M == 4 ? (const void *)kab_bandr_kernel<false> : (const void *)kab_bandr_kernel<true>))
                                   : (pl->band_q ? (const void *)kab_bandq_kernel : (const void *)kab_bandp_kernel);
       const int threads = pl->band_r ? KAB_BR_THREADS : (pl->band_q ? KAB_BQ_THREADS : KAB_BP_THREADS);
       if ((e = ensure_dyn_smem(fn, device, smem_b)) != cudaSuccess) { rc = cuda_fail(e, "cudaFuncSetAttribute(cluster band)"); break; }
       pl->smem[Q_BAND] = smem_b;
-      if (pl->band_nc > 8 && (e = cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)) != cudaSuccess) {
-        rc = cuda_fail(e, "cudaFuncSetAttribute(non-portable cluster size)"); break;
-      }
       cudaLaunchConfig_t cfg{};
       cudaLaunchAttribute at[1];
       at[0].id = cudaLaunchAttributeClusterDimension;
@@ -711,7 +732,7 @@ int kab_plan_run_device(kab_plan *pl, const float *d_log_probs, int32_t *d_best_
   if (pl->Vc) {
     KAB_CUDA(cudaMemsetAsync(pl->d_nonfinite, 0, (size_t)pl->B * sizeof(int32_t), stream));
     for (int q : fast_lists)
-      if (!pl->lists[q].empty()) {
+      if (!pl->lists[q].empty() && !(q == Q_BAND && pl->band_ga)) {
         const dim3 grid((unsigned)pl->lists[q].size(), (unsigned)((pl->max_T[q] + KAB_COMPACT_FRAMES - 1) / KAB_COMPACT_FRAMES));
         kab_compact_kernel<<<grid, 256, 0, stream>>>(pl->d_lists[q], d_log_probs, pl->d_lpc, pl->d_gather, pl->V, pl->Vc,
                                                      pl->d_nonfinite);
@@ -738,7 +759,8 @@ int kab_plan_run_device(kab_plan *pl, const float *d_log_probs, int32_t *d_best_
     }
   }
   if (!pl->lists[Q_BAND].empty()) {
-    KabParams pb = pf; pb.queue = pl->d_queue + Q_BAND;
+    KabParams pb = pl->band_ga ? p : pf; pb.queue = pl->d_queue + Q_BAND;
+    if (pl->band_ga) { pb.stage_frames = KAB_BR_F; pb.stage_bytes = 64; }  // (no emission stages: the geometry's minimum)
 #ifdef KAB_BAND_TIMING
     static long long *dbg = nullptr;
     if (!dbg) cudaMalloc((void **)&dbg, 32 * 8 * sizeof(long long));
@@ -872,12 +894,17 @@ int kab_plan_run_device(kab_plan *pl, const float *d_log_probs, int32_t *d_best_
         } rdbg_print{rdbg, stream, nwt};
 #endif
         if (pl->band_r) {
-          if (pl->M == 4)
+          if (pl->band_ga) {
+            if (pl->M == 4)
+              KAB_CUDA(cudaLaunchKernelEx(&cfg, kab_bandr_kernel<false, true>, (const KabLattice *)pl->d_lists[Q_BAND], n_band, pb));
+            else
+              KAB_CUDA(cudaLaunchKernelEx(&cfg, kab_bandr_kernel<true, true>, (const KabLattice *)pl->d_lists[Q_BAND], n_band, pb));
+          } else if (pl->M == 4)
             KAB_CUDA(cudaLaunchKernelEx(&cfg, kab_bandr_kernel<false>, (const KabLattice *)pl->d_lists[Q_BAND], n_band, pb));
           else
             KAB_CUDA(cudaLaunchKernelEx(&cfg, kab_bandr_kernel<true>, (const KabLattice *)pl->d_lists[Q_BAND], n_band, pb));
           const dim3 fg((unsigned)n_band, (unsigned)((pl->max_T[Q_BAND] + KAB_FIN_ROWS - 1) / KAB_FIN_ROWS));
-          kab_finite_rows_kernel<<<fg, 256, 0, stream>>>(pl->d_lists[Q_BAND], pf.lp, pf.V, d_status, d_final_score);
+          kab_finite_rows_kernel<<<fg, 256, 0, stream>>>(pl->d_lists[Q_BAND], pb.lp, pb.V, d_status, d_final_score);
         } else
           KAB_CUDA(cudaLaunchKernelEx(&cfg, kab_bandq_kernel, (const KabLattice *)pl->d_lists[Q_BAND], n_band, pb));
         kab_bt_maps_kernel<KabBtLayoutQ><<<mg, KAB_BT_THREADS, 0, stream>>>(pl->d_lists[Q_BAND], pl->d_bt_meta, n_band, pl->d_bp,
@@ -954,7 +981,7 @@ int kab_plan_run_device(kab_plan *pl, const float *d_log_probs, int32_t *d_best_
   }
   if (pl->Vc)  // best_labels of the staged kernels: compact index -> label value
     for (int q : fast_lists)
-      if (!pl->lists[q].empty()) {
+      if (!pl->lists[q].empty() && !(q == Q_BAND && pl->band_ga)) {
         const dim3 grid((unsigned)pl->lists[q].size(), (unsigned)((pl->max_T[q] + KAB_COMPACT_FRAMES - 1) / KAB_COMPACT_FRAMES));
         kab_expand_labels_kernel<<<grid, 64, 0, stream>>>(pl->d_lists[q], d_best_labels, d_status, d_final_score,
                                                           pl->d_gather, pl->Vc, pl->d_nonfinite);

@@ -129,7 +129,11 @@ __device__ __forceinline__ void kab_mbar_arrive_addr(uint32_t bar) {  // (32-bit
 #define KAB_RTM_ADD(acc, a, b)
 #endif
 
-template <bool MM>
+// GA ("gather"): the prep warps read the emissions straight from the log-probs in global memory
+// (L2) instead of staged rows -- for vocabularies whose rows do not fit a stage (V > 512) and
+// lattices with any number of distinct labels: no compact copy, no limit on V; the producer warp
+// then only writes the window table.
+template <bool MM, bool GA = false>
 __global__ void __launch_bounds__(KAB_BR_THREADS, 1)
     kab_bandr_kernel(const KabLattice *__restrict__ lats, int n_lat, KabParams p) {
   constexpr int G = KAB_BAND_G, GH = KAB_BR_GH, OW = KAB_BR_OW;
@@ -254,7 +258,9 @@ __global__ void __launch_bounds__(KAB_BR_THREADS, 1)
         wq += wqF; wr += wrF;          // S * (i + F) = (q + qF) * T + (r + rF), carried
         if (wr >= T) { wr -= T; ++wq; }
         __syncwarp();  // (the arming arrive below releases these words together with the rows)
-        if (c + 1 < n_chunks) {
+        if (GA) {
+          if (lane == 0) kab_mbar_arrive(&efull[stg]);  // the window table of this chunk is ready
+        } else if (c + 1 < n_chunks) {
           if (lane == 0) {
             kab_mbar_expect_tx(&efull[stg], full_bytes);
             kab_bulk_g2s(dst, lp_base + (size_t)c * chunk_stride, full_bytes, &efull[stg]);
@@ -335,7 +341,11 @@ __global__ void __launch_bounds__(KAB_BR_THREADS, 1)
         }
         KAB_RTM(pb);
         KAB_RTM_ADD(pm_wait, pa, pb);
-        const char *rowc = reinterpret_cast<const char *>(stage_base + st * stage_words + skew);
+        const char *rowc = GA ? reinterpret_cast<const char *>(p.lp + (lat.t_off + (int64_t)c * F) * V)
+                              : reinterpret_cast<const char *>(stage_base + st * stage_words + skew);
+        auto emission = [&](const char *a) -> float {
+          return GA ? __ldg(reinterpret_cast<const float *>(a)) : *reinterpret_cast<const float *>(a);
+        };
 #pragma unroll
         for (int gi = 0; gi < KAB_BR_F / G; ++gi, rowc += G * VB) {
           const int g = g0 + gi;
@@ -380,8 +390,7 @@ __global__ void __launch_bounds__(KAB_BR_THREADS, 1)
           if (safe) {
 #pragma unroll
             for (int f = 0; f < G; ++f)
-              tile[f * 32] = make_float2(*reinterpret_cast<const float *>(rowc + f * VB),
-                                         *reinterpret_cast<const float *>(rowc + f * VB + c1));
+              tile[f * 32] = make_float2(emission(rowc + f * VB), emission(rowc + f * VB + c1));
           } else {
             // edge warp (or the last, partial group): the exact per-frame window turned into masked emissions
             const int *wl = wtab + st * 32 + gi * G;
@@ -392,8 +401,8 @@ __global__ void __launch_bounds__(KAB_BR_THREADS, 1)
               const unsigned a = (unsigned)(vb - lo), wd = (unsigned)(hi - lo);
               float xb = ninf, x1 = ninf;
               if (f < nfr) {
-                xb = *reinterpret_cast<const float *>(rowc + f * VB);
-                x1 = *reinterpret_cast<const float *>(rowc + f * VB + c1);
+                xb = emission(rowc + f * VB);
+                x1 = emission(rowc + f * VB + c1);
               }
               tile[f * 32] = make_float2((a + 0u < wd) ? xb : ninf, (a + 1u < wd) ? x1 : ninf);
             }

@@ -267,16 +267,62 @@ def test_wide_vocabularies(kab, V):
     assert info.n_class[0] == 2 and info.n_class[1] == 2 and info.n_class[2] == 0
 
 
-def test_wide_vocabulary_too_many_labels(kab):
-    """More than 511 distinct labels in one lattice: no compact copy, the generic kernel takes the
-    plan (still bit-exact)."""
+def test_wide_vocabulary_too_many_labels(kab, monkeypatch):
+    """More than 511 distinct labels in one lattice: no compact copy is possible.  A band-shaped
+    lattice then runs kab_bandr_kernel in its gather mode (emissions straight from the caller's
+    log-probs), the short one next to it still goes through the compact copy; with the gather mode
+    switched off the generic kernel takes the plan.  Bit-exact either way."""
     from kokoro_align_b200 import synth
     T = np.array([2500, 300])
     L = np.array([900, 40])
     lp, t_off, labels, l_off = synth.make_batch(T, L, V=4096, seed=5200)
     assert len(np.unique(labels[:900])) > 511
     info = _compare_batch(kab, lp, t_off, labels, l_off, V=4096)
+    assert info.n_class[0] == 1 and info.n_class[1] == 1 and info.n_class[2] == 0
+    monkeypatch.setenv("KAB_BAND_GATHER", "0")
+    info = _compare_batch(kab, lp, t_off, labels, l_off, V=4096)
     assert info.n_class[2] == 2
+
+
+@pytest.mark.parametrize("max_move", [4, 3, 2])
+def test_wide_vocabulary_gather_mode_batch(kab, max_move):
+    """BASELINE config 5 with a BPE-sized vocabulary: several chapter-like lattices with thousands
+    of distinct labels (more lattices than resident clusters' worth of work-queue items), ties from
+    quantised log-probs, edge windows at both ends, next to segment-sized lattices of the same
+    vocabulary -- gather-mode band kernel + compact warp kernel in one plan."""
+    from kokoro_align_b200 import synth
+    T = np.array([9000, 150, 4001, 12000, 640, 2999, 8])
+    L = np.array([2500, 20, 1300, 1500, 90, 1000, 1])
+    lp, t_off, labels, l_off = synth.make_batch(T, L, V=4096, seed=5300 + max_move)
+    lp = (np.round(lp * 4) / 4).astype(np.float32)
+    assert len(np.unique(labels[:2500])) > 511
+    info = _compare_batch(kab, lp, t_off, labels, l_off, beam_size=700, max_move=max_move, V=4096)
+    assert info.n_class[1] == 4 and info.n_class[2] == 0
+
+
+def test_wide_vocabulary_gather_mode_nonfinite_and_bad_label(kab):
+    """Gather mode keeps the error contract: a non-finite value anywhere in a lattice's rows (also in
+    a column it never reads) is status 3, an out-of-range label status 2, the others are aligned."""
+    from kokoro_align_b200 import synth
+    from oracle import ctc_oracle
+    T = np.array([3000, 2000, 2500])
+    L = np.array([800, 600, 700])
+    V = 1500
+    lp, t_off, labels, l_off = synth.make_batch(T, L, V=V, seed=5400)
+    lp[1234, 77 if 77 not in labels[:800] else 78] = np.nan
+    labels = labels.copy()
+    labels[800 + 10] = V + 3
+    rst = ctc_oracle.ctc_best_path_batch(lp, t_off, labels, l_off, 400, 4, n_threads=2)[4]
+    with kab.AlignPlan(t_off, labels, l_off, V, 400) as plan:
+        path, labs, scores, final, status = plan.run_host(lp)
+        assert plan.info.n_class[1] == 2
+    np.testing.assert_array_equal(status, rst)
+    assert list(status) == [3, 2, 0]
+    rp, rl, rs, rf, _ = ctc_oracle.ctc_best_path_batch(lp, t_off, labels, l_off, 400, 4, n_threads=2)
+    a = int(t_off[2])
+    np.testing.assert_array_equal(path[a:], rp[a:])
+    np.testing.assert_array_equal(labs[a:], rl[a:])
+    assert scores[a:].tobytes() == rs[a:].tobytes() and final[2].tobytes() == rf[2].tobytes()
 
 
 def test_config4_banded_million_frames(kab):

@@ -21,8 +21,10 @@ if os.path.exists("MEASURED_PEAKS.json"):
 out = []
 points = [(T, L, 39) for T in Ts for L in Ls]
 # wide vocabularies (whole rows are staged up to V = 512)
-# (V = 4096: compact per-lattice copy of the used columns, kab_compact.cuh)
-wide_v = [(1000, 100, 256), (10000, 1000, 256), (1000, 100, 512), (1000, 100, 4096), (10000, 1000, 4096)]
+# (V = 4096: compact per-lattice copy of the used columns for the short lattices, kab_compact.cuh; the
+# band-shaped ones -- more than 511 distinct labels from L = 1000 on -- in kab_bandr.cuh's gather mode)
+wide_v = [(1000, 100, 256), (10000, 1000, 256), (1000, 100, 512), (1000, 100, 4096), (10000, 1000, 4096),
+          (100000, 10000, 4096)]
 points = wide_v if "--wide-v" in sys.argv else points + ([] if quick else wide_v)
 unbanded = "--unbanded" in sys.argv   # beam_size covers the lattice (config 5: where T*S <= 1e11)
 if unbanded:
