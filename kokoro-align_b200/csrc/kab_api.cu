@@ -496,12 +496,12 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
     const int want_r = re ? atoi(re) : -1;
     const int64_t n_band = (int64_t)pl->lists[Q_BAND].size();
     // Which kernel for this plan?  A makespan estimate from measured per-frame costs (B200, 1000-wide
-    // band): kab_bandr.cuh ~108 ns per frame on one of sm_count / ncr clusters that pull lattices from
+    // band): kab_bandr.cuh ~70 ns per frame on one of sm_count / ncr clusters that pull lattices from
     // the work queue, kab_band.cuh ~190 ns per frame with two lattices per SM.  A book (36 chapters)
     // is bound by its longest chapter -> bandr; hundreds of chapters at once -> the single-CTA kernel.
     double sum_t = 0.0, max_t = 0.0;
     for (const KabLattice &d : pl->lists[Q_BAND]) { sum_t += d.T; max_t = std::max(max_t, (double)d.T); }
-    const double est_r = std::max(max_t, sum_t / std::max(1, pl->sm_count / std::max(1, ncr))) * 108.0;
+    const double est_r = std::max(max_t, sum_t / std::max(1, pl->sm_count / std::max(1, ncr))) * 70.0;
     const double est_b = std::max(max_t, sum_t / (double)(pl->sm_count * (pl->band_nw <= 16 ? 2 : 1))) * 190.0;
     const bool use_r = pl->band_ga || (r_ok && want_r != 0 && want_nc != 0 && want_q != 0 && (want_r >= 1 || want_nc >= 1 || est_r <= est_b));
     const bool use_q = !use_r && M == 4 && q_ok && want_q != 0 && want_nc != 0 && (want_q >= 1 || n_band <= pl->sm_count / ncq);

@@ -46,6 +46,7 @@
 #define KAB_BR_F 16           // frames per emission stage this kernel is built for (two groups; the plan checks it)
 #define KAB_BR_TD 8           // emission tiles per compute warp (groups the prep warps may run ahead)
 #define KAB_BR_MD 16          // mailbox depth (messages)
+#define KAB_BR_GA_AHEAD 12    // gather mode: chunks (of 16 frames) the L2 prefetch runs ahead of the producer
 #define KAB_BR_BG 16          // groups per backpointer block (2 KB)
 #define KAB_BR_NBB 4          // backpointer staging buffers per compute warp
 #ifdef KAB_BR_ISOLATE          // experiment: 2 compute warps alone on schedulers 0 and 1, the helpers on 2 and 3
@@ -259,7 +260,22 @@ __global__ void __launch_bounds__(KAB_BR_THREADS, 1)
         if (wr >= T) { wr -= T; ++wq; }
         __syncwarp();  // (the arming arrive below releases these words together with the rows)
         if (GA) {
-          if (lane == 0) kab_mbar_arrive(&efull[stg]);  // the window table of this chunk is ready
+          // The rows themselves go to L2 ahead of the prep warps' gathers: the first warp to reach a chunk
+          // would otherwise pay the DRAM latency once per tile.  Each CTA of the cluster prefetches its
+          // 1 / NC of the chunk that is KAB_BR_GA_AHEAD chunks ahead (one bulk-prefetch instruction).
+          if (lane == 0) {
+            const int c_first = c == 0 ? 0 : c + KAB_BR_GA_AHEAD, c_last = min(n_chunks - 1, c + KAB_BR_GA_AHEAD);
+            for (int cp = c_first; cp <= c_last; ++cp) {
+              const int64_t row0 = lat.t_off + (int64_t)cp * F;
+              const uint64_t base = reinterpret_cast<uint64_t>(p.lp);  // (absolute addresses: 16-byte alignment is the instruction's)
+              const uint64_t b0 = base + (uint64_t)(row0 * V * 4), b1 = base + (uint64_t)((row0 + min(F, T - cp * F)) * V * 4);
+              const uint64_t part = (((b1 - b0 + NC - 1) / NC) + 15) & ~(uint64_t)15;
+              const uint64_t a0 = (b0 + (uint64_t)rank * part) & ~(uint64_t)15;
+              const uint64_t a1 = min(min(a0 + part + 16, b1), base + (uint64_t)p.lp_bytes) & ~(uint64_t)15;
+              if (a1 > a0) kab_bulk_prefetch_l2(reinterpret_cast<const void *>(a0), (uint32_t)(a1 - a0));
+            }
+            kab_mbar_arrive(&efull[stg]);  // the window table of this chunk is ready
+          }
         } else if (c + 1 < n_chunks) {
           if (lane == 0) {
             kab_mbar_expect_tx(&efull[stg], full_bytes);

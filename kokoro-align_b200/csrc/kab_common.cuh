@@ -100,6 +100,10 @@ __device__ __forceinline__ void kab_bulk_g2s(void *dst, const void *src, uint32_
                "l"(src), "r"(bytes), "r"(kab_smem_u32(bar))
                : "memory");
 }
+// Bulk prefetch of a global range into L2 (no destination): address 16-byte aligned, size a multiple of 16.
+__device__ __forceinline__ void kab_bulk_prefetch_l2(const void *src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 // Same, with an L2 eviction-priority hint (createpolicy); the warp kernel passes evict_normal.
 __device__ __forceinline__ void kab_bulk_g2s_hint(void *dst, const void *src, uint32_t bytes, uint64_t *bar,
                                                   uint64_t policy) {
