@@ -573,7 +573,7 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
       m.first_block = pl->bt_blocks;
       m.n_blocks = (d.T + KAB_BT_BLOCK - 1) / KAB_BT_BLOCK;
       m.wl = (int32_t)align_up(std::min<int64_t>(W, 2 * (int64_t)d.L + 1), 32);
-      pl->bt_map_ints += (int64_t)m.n_blocks * m.wl;
+      pl->bt_map_ints += (int64_t)m.n_blocks * KAB_BT_NSUB * m.wl;
       pl->bt_blocks += m.n_blocks;
       pl->bt_max_wl = std::max(pl->bt_max_wl, m.wl);
       pl->bt_meta.push_back(m);

@@ -8,14 +8,18 @@
 // exactly -- no speculation:
 //   1. kab_bt_maps_kernel: the frames are cut into blocks of KAB_BT_BLOCK frames.  For every block and
 //      EVERY state of the window at the block's last frame, one thread walks the block backwards
-//      and records where it leaves it: maps[block][v - lo] = state at the frame before the block.
+//      and records where it leaves it: maps[block][0][v - lo] = state at the frame before the block
+//      (and, in passing, where it stands after every KAB_BT_SUB frames: maps[block][q][v - lo], q > 0,
+//      is its state at the frame before sub-block q).
 //      T x W steps in total (as many as the forward pass has cells), spread over the whole GPU.
 //      Walkers that start in inactive states produce values nobody looks up (their addresses are
 //      derived from the ring position, which always stays inside the workspace).
 //   2. kab_bt_stitch_kernel (one CTA per lattice): thread 0 composes the maps from the forced end
 //      state down -- T / KAB_BT_BLOCK dependent table look-ups -- which yields the true entry
 //      state of every block; then the threads re-walk the blocks from their entry states, all
-//      blocks at once (best_path);
+//      blocks at once and every block as KAB_BT_NSUB sub-blocks whose entry states are one look-up in
+//      the same maps (best_path): a lone walker costs ~330 cycles per frame, so the re-walk is the
+//      length of ONE sub-block;
 //   3. kab_bt_gather_kernel: best_labels and best_scores of the path (align.py:105-107), coalesced
 //      over the frames.
 // Backpointer layouts (template parameter of the kernels):
@@ -34,24 +38,29 @@ struct KabBtLayoutP {
   static constexpr int OW = KAB_BAND_OW;  // ring slots per warp region
   static constexpr int GROW = 256;        // bytes per region and 8-frame group
   static __device__ __forceinline__ int move(const unsigned char *gp, int rs, int f) {
-    const unsigned int byte = gp[((rs >> 2) << 3) + f];
+    const unsigned int byte = __ldg(gp + ((rs >> 2) << 3) + f);  // (read-only here: the forward kernel wrote it)
     return (int)((byte >> (2 * (rs & 3))) & 3u);
   }
+  static __device__ __forceinline__ int byte_off(int rs) { return (rs >> 2) << 3; }  // of the state's codes inside a group's row
 };
 struct KabBtLayoutQ {
   static constexpr int OW = KAB_BQ_OW;
   static constexpr int GROW = 128;
   static __device__ __forceinline__ int move(const unsigned char *gp, int rs, int f) {
-    const uint32_t word = *reinterpret_cast<const uint32_t *>(gp + (KAB_BQ_GH + (rs >> 1)) * 4);
+    const uint32_t word = __ldg(reinterpret_cast<const uint32_t *>(gp + (KAB_BQ_GH + (rs >> 1)) * 4));
     return (int)((word >> (4 * f + 2 * (rs & 1))) & 3u);
   }
+  static __device__ __forceinline__ int byte_off(int rs) { return (KAB_BQ_GH + (rs >> 1)) * 4; }
 };
 
 #define KAB_BT_BLOCK 1024   // frames per block
+#define KAB_BT_SUB 256      // frames per sub-block of the re-walk (128: 138 -> 126 us on Gon gitsune, twice the maps)
+#define KAB_BT_NSUB (KAB_BT_BLOCK / KAB_BT_SUB)
 #define KAB_BT_THREADS 128  // threads per CTA of the map kernel (= entry states per CTA)
+#define KAB_BT_PF_AHEAD 6    // groups a lone walker prefetches ahead
 
 struct KabBtMeta {       // one per lattice of the band list (same order)
-  int64_t map_off;       // first int32 of this lattice's maps
+  int64_t map_off;       // first int32 of this lattice's maps ([n_blocks][KAB_BT_NSUB][wl])
   int32_t first_block;   // prefix sum of n_blocks over the list
   int32_t n_blocks;
   int32_t wl;            // map row length: min(W, S) rounded up to 32
@@ -95,16 +104,34 @@ struct KabBtWalker {
     }
     return at;
   }
-  // frames te .. t0 (t0 a multiple of 8), descending; f(t, state at t) for every frame
-  template <class F>
+  // frames te .. t0 (t0 a multiple of 8), descending; f(t, state at t) for every frame.
+  // PF: a LONE walker (the stitch kernel's re-walk: one thread per block, nothing to hide the latency
+  // behind) prefetches the rows of the groups it will reach -- a group's row of this region is one
+  // 128 / 256-byte line whatever the state, so the address is known ahead -- and then pays L1 hits
+  // instead of one L2 round trip per group (measured: 345 -> see DESIGN.md section 3.4).
+  template <bool PF = false, class F>
   __device__ __forceinline__ void walk(int te, int t0, int NWT, int64_t stride, F f) {
     int g = te >> 3;
+    const int g0 = t0 >> 3;
+    // (the sector the walker is heading for and the one below it: a path climbs ~2 states per group,
+    // 24 at most, and a state is 2 bytes of a row in both layouts)
+    auto prefetch_row = [&](int ahead) {
+      const unsigned char *a = gp - (size_t)ahead * LY::GROW + (LY::byte_off(rs) & ~31);
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
+      if (LY::byte_off(rs) >= 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(a - 32));
+    };
+    if (PF) {
+#pragma unroll
+      for (int a = 1; a < KAB_BT_PF_AHEAD; ++a)
+        if (g - a >= g0) prefetch_row(a);
+    }
     if ((te & 7) != 7) {  // partial group at the top (the last frames of the lattice)
       for (int k = te & 7; k >= 0; --k) f(g * 8 + k, step(k, NWT, stride));
       --g;
       gp -= LY::GROW;
     }
-    for (; g >= (t0 >> 3); --g, gp -= LY::GROW) {
+    for (; g >= g0; --g, gp -= LY::GROW) {
+      if (PF && g - KAB_BT_PF_AHEAD >= g0) prefetch_row(KAB_BT_PF_AHEAD);
 #pragma unroll
       for (int k = 7; k >= 0; --k) f(g * 8 + k, step(k, NWT, stride));
     }
@@ -137,8 +164,14 @@ kab_bt_maps_kernel(const KabLattice *__restrict__ lats, const KabBtMeta *__restr
   const int64_t stride = (int64_t)n_groups * LY::GROW;
   KabBtWalker<LY> w;
   w.init(lo + j, R, bp, stride, te >> 3);
-  w.walk(te, t0, NWT, stride, [](int, int) {});
-  maps[m.map_off + (int64_t)b * m.wl + j] = w.v;
+  int32_t *row = maps + m.map_off + (int64_t)b * KAB_BT_NSUB * m.wl + j;
+#pragma unroll 1
+  for (int q = KAB_BT_NSUB - 1; q >= 0; --q) {  // (the walker carries on where the sub-block above ended)
+    const int s0 = t0 + q * KAB_BT_SUB;
+    if (s0 > te) continue;
+    w.walk(min(te, s0 + KAB_BT_SUB - 1), s0, NWT, stride, [](int, int) {});
+    row[(int64_t)q * m.wl] = w.v;
+  }
 }
 
 // one CTA per lattice
@@ -156,26 +189,41 @@ kab_bt_stitch_kernel(const KabLattice *__restrict__ lats, const KabBtMeta *__res
   for (int b = threadIdx.x; b < m.n_blocks; b += blockDim.x)
     ent[b] = kab_bt_lo(S, min(T, (b + 1) * KAB_BT_BLOCK) - 1, T, W);
   __syncthreads();
+#ifdef KAB_BT_TIMING
+  const long long tt0 = clock64();
+#endif
   if (threadIdx.x == 0) {  // compose the block maps from the forced end state down: one L2 load per block
     int v = end_state[lat.index];
     for (int b = m.n_blocks - 1; b >= 0; --b) {
       const int lo = ent[b];
       ent[b] = v;
-      v = __ldcg(&maps[m.map_off + (int64_t)b * m.wl + (v - lo)]);
+      v = __ldcg(&maps[m.map_off + (int64_t)b * KAB_BT_NSUB * m.wl + (v - lo)]);
     }
   }
   __syncthreads();
+#ifdef KAB_BT_TIMING
+  const long long tt1 = clock64();
+#endif
   // every block re-walked from its entry state, one thread each: only the backpointer bytes are on
   // the dependent chain (eight frames share a sector)
   const unsigned char *bp = p.bp + lat.bp_off;
   const int64_t stride = (int64_t)n_groups * LY::GROW;
   int32_t *out_path = p.best_path + lat.t_off;
-  for (int b = threadIdx.x; b < m.n_blocks; b += blockDim.x) {
+  for (int k = threadIdx.x; k < m.n_blocks * KAB_BT_NSUB; k += blockDim.x) {
+    const int b = k / KAB_BT_NSUB, q = k % KAB_BT_NSUB;
     const int t0 = b * KAB_BT_BLOCK, te = min(T, t0 + KAB_BT_BLOCK) - 1;
+    const int s0 = t0 + q * KAB_BT_SUB;
+    if (s0 > te) continue;
+    const int se = min(te, s0 + KAB_BT_SUB - 1);
+    int v0 = ent[b];  // the block's entry state; a lower sub-block starts where the walker from there left the one above
+    if (se != te) v0 = __ldcg(&maps[m.map_off + ((int64_t)b * KAB_BT_NSUB + q + 1) * m.wl + (v0 - kab_bt_lo(S, te, T, W))]);
     KabBtWalker<LY> w;
-    w.init(ent[b], R, bp, stride, te >> 3);
-    w.walk(te, t0, NWT, stride, [&](int t, int at) { out_path[t] = at; });
+    w.init(v0, R, bp, stride, se >> 3);
+    w.template walk<true>(se, s0, NWT, stride, [&](int t, int at) { out_path[t] = at; });
   }
+#ifdef KAB_BT_TIMING
+  if (threadIdx.x < 3 || threadIdx.x == 79) printf("stitch thread %d: compose %lld cycles, walk %lld cycles (%d blocks)\n", threadIdx.x, tt1 - tt0, clock64() - tt1, m.n_blocks);
+#endif
 }
 
 // labels and scores of the path (align.py:105-107): grid (lattices, chunks of 4096 frames), coalesced
