@@ -1072,8 +1072,9 @@ static int segment_stats_launch(kab_plan *pl, const int32_t *d_path, const int32
                                 cudaStream_t stream) {
   if (n_seg > 0) {
     if (!pl->d_seg_scratch) KAB_CUDA(pool_malloc((void **)&pl->d_seg_scratch, (size_t)std::max<int64_t>(pl->total_T, 1) * 4));
-    const unsigned grid = (unsigned)std::min<int64_t>((n_seg + KAB_SEG_WARPS - 1) / KAB_SEG_WARPS, (int64_t)pl->sm_count * 8);
-    kab_segment_stats_kernel<<<grid, KAB_SEG_WARPS * 32, 0, stream>>>(n_seg, pl->B, d_seg_lat_off, d_seg_end, pl->d_t_off,
+    const unsigned grid = (unsigned)std::min<int64_t>((n_seg + KAB_SEG_WARPS - 1) / KAB_SEG_WARPS, (int64_t)pl->sm_count * 3);
+    KAB_CUDA(ensure_dyn_smem((const void *)kab_segment_stats_kernel, pl->device, KAB_SEG_SMEM));
+    kab_segment_stats_kernel<<<grid, KAB_SEG_WARPS * 32, KAB_SEG_SMEM, stream>>>(n_seg, pl->B, d_seg_lat_off, d_seg_end, pl->d_t_off,
                                                                       d_path, d_lab, d_sc, d_st, pl->d_seg_scratch, d_rec);
   }
   if (d_lab8 && pl->total_T > 0) {
