@@ -74,6 +74,8 @@ typedef struct kab_plan_info {
 #define KAB_BAND_KERNEL_CLUSTER 2  /* kab_bandp_kernel: cluster, four states per lane */
 #define KAB_BAND_KERNEL_CLUSTER2 3 /* kab_bandq_kernel: cluster, two states per lane */
 #define KAB_BAND_KERNEL_SPEC 4     /* kab_bandr_kernel: cluster, warp-specialised (prep warps, shared-memory mailboxes) */
+#define KAB_BAND_KERNEL_HYBRID 5   /* the longest lattices in kab_bandr_kernel clusters (band_cluster CTAs each), the others in
+                                      kab_band_kernel on the remaining SMs, side by side */
 
 int kab_version(void);
 const char *kab_error_string(int code);

@@ -33,7 +33,8 @@ class PlanInfo(ctypes.Structure):
                 ("kernel_launches", ctypes.c_int32), ("device", ctypes.c_int32),
                 ("band_kernel", ctypes.c_int32), ("band_cluster", ctypes.c_int32)]
 
-BAND_KERNELS = {0: None, 1: "kab_band_kernel", 2: "kab_bandp_kernel", 3: "kab_bandq_kernel", 4: "kab_bandr_kernel"}
+BAND_KERNELS = {0: None, 1: "kab_band_kernel", 2: "kab_bandp_kernel", 3: "kab_bandq_kernel", 4: "kab_bandr_kernel",
+                5: "kab_bandr_kernel for the longest lattices + kab_band_kernel"}
 
 
 class SegmentRecord(ctypes.Structure):

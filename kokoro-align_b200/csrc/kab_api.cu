@@ -142,6 +142,15 @@ struct kab_plan {
   int32_t band_nc = 0;  // > 0: a cluster band kernel (kab_bandp.cuh / kab_bandq.cuh) with clusters of band_nc CTAs
   bool band_q = false;  // the cluster kernel is kab_bandq_kernel / kab_bandr_kernel (two states per lane, KabBtLayoutQ)
   bool band_r = false;  // ... kab_bandr_kernel (warp-specialised: prep warps, shared-memory mailboxes)
+  // Hybrid band plan: the longest band lattices run in a sub-plan (kab_bandr.cuh, whole clusters: the
+  // shortest frame) on a side stream while this plan's single-CTA kernel (kab_band.cuh: the highest
+  // throughput) takes the others on the SMs that are left.
+  kab_plan *sub = nullptr;
+  cudaStream_t s_sub = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int32_t band_sm_reserved = 0;  // SMs left to the sub-plan's clusters
+  unsigned int *d_started = nullptr;  // sub-plan: CTAs of kab_bandr_kernel that have started, over all runs
+  unsigned int gate_target = 0;       // ... and the count the current run will bring it to
   bool band_ga = false;  // the band lattices run kab_bandr_kernel in its gather mode (V > 512: emissions straight from the
                          // caller's log-probs, any number of distinct labels, no compact copy)
   int32_t band_cw = 0;  // compute warps per CTA of that kernel (ring of 40 * band_cw * band_nc slots)
@@ -253,9 +262,14 @@ int plan_free(kab_plan *pl) {
   if (pl->stream) cudaStreamSynchronize(pl->stream);
   if (pl->s_out) cudaStreamSynchronize(pl->s_out);
   host_teardown(pl);
+  if (pl->s_sub) cudaStreamSynchronize(pl->s_sub);
+  if (pl->sub) plan_free(pl->sub);
+  if (pl->ev_fork) cudaEventDestroy(pl->ev_fork);
+  if (pl->ev_join) cudaEventDestroy(pl->ev_join);
+  if (pl->s_sub) cudaStreamDestroy(pl->s_sub);
   for (int q = 0; q < N_QUEUES; ++q) pool_free(pl->d_lists[q]);
   pool_free(pl->d_col16); pool_free(pl->d_raw); pool_free(pl->d_bp); pool_free(pl->d_scratch);
-  pool_free(pl->d_queue); pool_free(pl->d_status_init); pool_free(pl->d_wide_ws); pool_free(pl->d_band_fifo); pool_free(pl->d_bt_meta); pool_free(pl->d_bt_maps); pool_free(pl->d_bt_entry); pool_free(pl->d_end_state); pool_free(pl->d_gather); pool_free(pl->d_lpc); pool_free(pl->d_nonfinite); pool_free(pl->d_t_off); pool_free(pl->d_seg_scratch);
+  pool_free(pl->d_queue); pool_free(pl->d_status_init); pool_free(pl->d_wide_ws); pool_free(pl->d_band_fifo); pool_free(pl->d_bt_meta); pool_free(pl->d_bt_maps); pool_free(pl->d_bt_entry); pool_free(pl->d_end_state); pool_free(pl->d_gather); pool_free(pl->d_lpc); pool_free(pl->d_nonfinite); pool_free(pl->d_t_off); pool_free(pl->d_seg_scratch); pool_free(pl->d_started);
   delete pl;
   tr.mark("free");
   return KAB_OK;
@@ -286,8 +300,21 @@ int kab_device_count(int *count) {
   return KAB_OK;
 }
 
+namespace {
+// mask: only the lattices with mask[b] != 0 belong to this plan (nullptr: all); band_mode: -1 the
+// plan chooses (and may go hybrid), 0 the single-CTA band kernel, 1 kab_bandr.cuh
+int plan_create_impl(kab_plan **out, int device, int64_t B, const int64_t *t_off, const int32_t *labels,
+                     const int64_t *l_off, int32_t V, int32_t W, int32_t M, const uint8_t *mask, int band_mode);
+}  // namespace
+
 int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off, const int32_t *labels,
                     const int64_t *l_off, int32_t V, int32_t W, int32_t M) {
+  return plan_create_impl(out, device, B, t_off, labels, l_off, V, W, M, nullptr, -1);
+}
+
+namespace {
+int plan_create_impl(kab_plan **out, int device, int64_t B, const int64_t *t_off, const int32_t *labels,
+                     const int64_t *l_off, int32_t V, int32_t W, int32_t M, const uint8_t *mask, int band_mode) {
   if (!out || B < 0 || !t_off || !l_off || V < 1 || V > 65535 || W < 0 || M < 1 || M > 255) return KAB_E_BAD_ARG;
   if (B > 0 && (t_off[0] < 0 || l_off[0] < 0)) return KAB_E_BAD_ARG;
   if (B > 0 && l_off[B] > l_off[0] && !labels) return KAB_E_BAD_ARG;
@@ -327,6 +354,7 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
     const char *ge = getenv("KAB_BAND_GATHER");
     bool ok = V > MAX_STAGE_V && M <= 4 && !(ge && atoi(ge) == 0) && kab_bandr_geom(64).smem_bytes <= 227 * 1024, any_band = false;
     for (int64_t b = 0; b < B && ok; ++b) {
+      if (mask && !mask[b]) continue;
       const int64_t T = t_off[b + 1] - t_off[b], S = 2 * (l_off[b + 1] - l_off[b]) + 1;
       if (band_shaped(T, S)) { any_band = true; ok = std::min<int64_t>(W, S) <= ga_max_weff; }
     }
@@ -337,6 +365,7 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
     int64_t dmax = 0;
     bool any = false;
     for (int64_t b = 0; b < B; ++b) {
+      if (mask && !mask[b]) continue;
       const int64_t L = l_off[b + 1] - l_off[b];
       const int32_t *lab = labels + l_off[b];
       if (pl->band_ga && band_shaped(t_off[b + 1] - t_off[b], 2 * L + 1)) continue;  // (not through the compact copy)
@@ -383,11 +412,14 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
   std::vector<int32_t> status_init((size_t)B, 0);
   col16.reserve((size_t)(pl->total_L + 16 * B + 16));
   int64_t bp_bytes = 0, scr_floats = 0, max_band_weff = 0;
+  std::vector<uint8_t> hyb_mask;  // hybrid band plan: the lattices of the sub-plan
+  int hyb_k = 0;                  // ... and its clusters
   kab_plan_info &info = pl->info;
   info.n_lattices = B; info.device = device; info.total_frames = pl->total_T;
   std::vector<int64_t> distinct_words(1024, 0);
   const int n_mask = (V + 63) / 64;
   for (int64_t b = 0; b < B; ++b) {
+    if (mask && !mask[b]) continue;
     const int64_t T = t_off[b + 1] - t_off[b], L = l_off[b + 1] - l_off[b], S = 2 * L + 1;
     const int32_t *lab = labels + l_off[b];
     bool bad = false, special = false;
@@ -478,6 +510,7 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
     const int nc = (pl->band_nw + KAB_BP_CW - 1) / KAB_BP_CW;
     const char *cl = getenv("KAB_BAND_CLUSTER");
     int want_nc = cl ? atoi(cl) : -1;
+    if (band_mode >= 0) want_nc = band_mode == 0 ? 0 : -1;  // (sub-plans of a hybrid plan: the kernel is given)
     const bool cluster_ok = nc <= 8 && kab_bandp_geom(pl->stage_bytes).smem_bytes <= 227 * 1024;
     // kab_bandq.cuh (two warps per scheduler, two states per lane: the shorter frame) when its ring
     // of 40-slot warps fits a cluster of <= 8 CTAs and every lattice gets its own cluster at once;
@@ -492,10 +525,10 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
     const int ncr = (nwq + KAB_BR_CW - 1) / KAB_BR_CW;
     const bool r_ok = pl->band_ga || (ncr <= 8 && pl->stage_frames == KAB_BR_F && kab_bandr_geom(pl->stage_bytes).smem_bytes <= 227 * 1024);
     const char *qe = getenv("KAB_BAND_Q");
-    const int want_q = qe ? atoi(qe) : -1;
+    const int want_q = band_mode >= 0 ? (band_mode == 0 ? 0 : -1) : (qe ? atoi(qe) : -1);
     const char *re = getenv("KAB_BAND_R");
-    const int want_r = re ? atoi(re) : -1;
-    const int64_t n_band = (int64_t)pl->lists[Q_BAND].size();
+    const int want_r = band_mode >= 0 ? band_mode : (re ? atoi(re) : -1);
+    int64_t n_band = (int64_t)pl->lists[Q_BAND].size();
     // Which kernel for this plan?  A makespan estimate from measured per-frame costs (B200, 1000-wide
     // band): kab_bandr.cuh ~70 ns per frame on one of sm_count / ncr clusters that pull lattices from
     // the work queue, kab_band.cuh ~190 ns per frame with two lattices per SM.  A book (36 chapters)
@@ -506,6 +539,46 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
     const double est_b = std::max(max_t, sum_t / (double)(pl->sm_count * (pl->band_nw <= 16 ? 2 : 1))) * 190.0;
     const bool use_r = pl->band_ga || (r_ok && want_r != 0 && want_nc != 0 && want_q != 0 && (want_r >= 1 || want_nc >= 1 || est_r <= est_b));
     const bool use_q = !use_r && M == 4 && q_ok && want_q != 0 && want_nc != 0 && (want_q >= 1 || n_band <= pl->sm_count / ncq);
+    // Hybrid: a plan of hundreds of chapters takes the single-CTA kernel (throughput), but its makespan
+    // is then the LONGEST chapter at that kernel's 190 ns per frame.  Give the longest ones to
+    // kab_bandr.cuh (70 ns per frame) on k clusters and the rest to the single-CTA kernel on the other
+    // SMs, side by side: the split (k clusters, the m longest lattices) with the smallest estimated
+    // makespan, taken when it beats the single kernel by 15 %.  KAB_BAND_HYBRID=0 / 1 disables / forces it.
+    {
+      const char *he = getenv("KAB_BAND_HYBRID");
+      const int want_h = he ? atoi(he) : -1;
+      if (band_mode < 0 && !mask && !use_r && !use_q && r_ok && !pl->band_ga && !pl->Vc && V <= MAX_STAGE_V && want_h != 0 &&
+          want_r < 0 && want_q < 0 && want_nc < 0 && n_band >= 2) {
+        std::vector<KabLattice> &bl = pl->lists[Q_BAND];
+        std::stable_sort(bl.begin(), bl.end(), [](const KabLattice &a, const KabLattice &b2) { return a.T > b2.T; });
+        std::vector<double> pre((size_t)n_band + 1, 0.0);
+        for (int64_t i = 0; i < n_band; ++i) pre[(size_t)i + 1] = pre[(size_t)i] + bl[(size_t)i].T;
+        const int per_sm = pl->band_nw <= 16 ? 2 : 1;
+        double best = est_b;
+        int best_k = 0;
+        int64_t best_m = 0;
+        for (int k = 1; k <= pl->sm_count / ncr / 2; ++k) {
+          const double sm_left = (double)(pl->sm_count - k * ncr) * per_sm;
+          for (int64_t m = k; m < n_band && m <= 16 * (int64_t)k; ++m) {
+            const double tr_ = std::max((double)bl[0].T, pre[(size_t)m] / k) * 70.0;
+            const double tb_ = std::max((double)bl[(size_t)m].T, (sum_t - pre[(size_t)m]) / sm_left) * 190.0;
+            const double ms = std::max(tr_, tb_);
+            if (ms < best) { best = ms; best_k = k; best_m = m; }
+          }
+        }
+        if (want_h >= 1 && best_k == 0) { best_k = 1; best_m = 1; }
+        if (best_k > 0 && (want_h >= 1 || best < 0.85 * est_b)) {
+          hyb_mask.assign((size_t)B, 0);
+          for (int64_t i = 0; i < best_m; ++i) hyb_mask[(size_t)bl[(size_t)i].index] = 1;
+          bl.erase(bl.begin(), bl.begin() + best_m);
+          hyb_k = best_k;
+          want_nc = 0;  // (the rest: the single-CTA kernel, whatever its number)
+          pl->band_sm_reserved = best_k * ncr;
+          n_band = (int64_t)bl.size();
+          pl->max_T[Q_BAND] = bl.empty() ? 0 : bl[0].T;
+        }
+      }
+    }
     if (use_r || use_q) {
       pl->band_q = true;
       pl->band_r = use_r;
@@ -665,7 +738,7 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
       int occ = 0;
       if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, pl->band_nw * 32, geo.smem_bytes)) != cudaSuccess) { rc = cuda_fail(e, "occupancy(band)"); break; }
       pl->smem[Q_BAND] = geo.smem_bytes;
-      pl->grid[Q_BAND] = (int)std::min<int64_t>((int64_t)pl->lists[Q_BAND].size(), (int64_t)pl->sm_count * std::max(occ, 1));
+      pl->grid[Q_BAND] = (int)std::min<int64_t>((int64_t)pl->lists[Q_BAND].size(), (int64_t)(pl->sm_count - pl->band_sm_reserved) * std::max(occ, 1));
     }
     if (!pl->lists[Q_WIDE].empty()) {
       if ((e = pool_malloc((void **)&pl->d_wide_ws, (size_t)pl->wide_ws_bytes)) != cudaSuccess) { rc = cuda_fail(e, "pool_malloc(wide workspace)"); break; }
@@ -691,9 +764,29 @@ int kab_plan_create(kab_plan **out, int device, int64_t B, const int64_t *t_off,
   if (pl->band_r) info.kernel_launches += 1;            // kab_finite_rows_kernel
   if (pl->Vc)                                          // kab_compact_kernel, kab_expand_labels_kernel
     for (int q : {Q_WARP, Q_BAND, Q_WIDE}) info.kernel_launches += pl->lists[q].empty() ? 0 : 2;
+  if (hyb_k > 0) {  // the sub-plan of a hybrid band plan: same arrays, its own lattices, workspaces and stream
+    int rcs = plan_create_impl(&pl->sub, device, B, t_off, labels, l_off, V, W, M, hyb_mask.data(), 1);
+    if (rcs == KAB_OK) {
+      pl->sub->is_child = true;
+      pl->sub->grid[Q_BAND] = std::min(pl->sub->grid[Q_BAND], hyb_k * pl->sub->band_nc);
+      cudaError_t e = pool_malloc((void **)&pl->sub->d_started, sizeof(unsigned int));
+      if (e == cudaSuccess) e = cudaMemset(pl->sub->d_started, 0, sizeof(unsigned int));
+      if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&pl->s_sub, cudaStreamNonBlocking);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->ev_fork, cudaEventDisableTiming);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->ev_join, cudaEventDisableTiming);
+      if (e != cudaSuccess) rcs = cuda_fail(e, "stream / events of the hybrid band plan");
+    }
+    if (rcs != KAB_OK) { plan_free(pl); return rcs; }
+    info.band_kernel = KAB_BAND_KERNEL_HYBRID;
+    info.band_cluster = pl->sub->band_nc;
+    info.backptr_bytes += pl->sub->info.backptr_bytes;
+    info.workspace_bytes += pl->sub->info.workspace_bytes;
+    info.kernel_launches += pl->sub->info.kernel_launches;
+  }
   *out = pl;
   return KAB_OK;
 }
+}  // namespace
 
 int kab_plan_get_info(const kab_plan *pl, kab_plan_info *info) {
   if (!pl || !info) return KAB_E_BAD_ARG;
@@ -721,6 +814,7 @@ int kab_plan_run_device(kab_plan *pl, const float *d_log_probs, int32_t *d_best_
   p.V = pl->V; p.W = pl->W; p.M = pl->M;
   p.stage_frames = pl->stage_frames; p.stage_bytes = pl->stage_bytes;
   p.one = 1u;
+  p.started = pl->d_started;
   {  // max_move < 4: the excluded moves' candidates become -inf (kab_mm)
     const float ninf = -std::numeric_limits<float>::infinity();
     p.mm1 = pl->M >= 2 ? 0.0f : ninf; p.mm2 = pl->M >= 3 ? 0.0f : ninf; p.mm3 = pl->M >= 4 ? 0.0f : ninf;
@@ -743,6 +837,17 @@ int kab_plan_run_device(kab_plan *pl, const float *d_log_probs, int32_t *d_best_
     pf.lp_bytes = pl->total_T * (int64_t)pl->Vc * 4;
   }
 
+  if (pl->sub) {  // hybrid band plan: the long lattices first (their clusters need whole SMs), on the side stream
+    KAB_CUDA(cudaEventRecord(pl->ev_fork, stream));
+    KAB_CUDA(cudaStreamWaitEvent(pl->s_sub, pl->ev_fork, 0));
+    if (int rcs = kab_plan_run_device(pl->sub, d_log_probs, d_best_path, d_best_labels, d_best_scores, d_final_score, d_status, pl->s_sub))
+      return rcs;
+    KAB_CUDA(cudaEventRecord(pl->ev_join, pl->s_sub));
+    // the single-CTA kernel below would otherwise spread one CTA over every SM before the clusters
+    // (which need whole SMs) are placed, and the two kernels would run one after the other
+    pl->sub->gate_target += (unsigned int)pl->sub->grid[Q_BAND];
+    if (!pl->lists[Q_BAND].empty()) kab_gate_kernel<<<1, 32, 0, stream>>>(pl->sub->d_started, pl->sub->gate_target);
+  }
   KAB_CUDA(cudaMemsetAsync(pl->d_queue, 0, N_QUEUES * sizeof(unsigned int), stream));
   if (pl->any_bad_label)
     KAB_CUDA(cudaMemcpyAsync(d_status, pl->d_status_init, (size_t)pl->B * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
@@ -993,6 +1098,7 @@ int kab_plan_run_device(kab_plan *pl, const float *d_log_probs, int32_t *d_best_
         pl->d_lists[Q_GENERIC], (int)pl->lists[Q_GENERIC].size(), pg);
   }
   KAB_CUDA(cudaGetLastError());
+  if (pl->sub) KAB_CUDA(cudaStreamWaitEvent(stream, pl->ev_join, 0));
   return record_run_event(pl, stream);
 }
 

@@ -49,7 +49,22 @@ struct KabParams {
   float mm1, mm2, mm3;      // max_move < 4 (the MM instantiations of the staged kernels): 0 or -inf, added to the
                             // candidates of moves 1 / 2 / 3 -- a candidate that max_move excludes (align.py:70)
                             // becomes -inf, which is what "no candidate" is everywhere else
+  unsigned int *started;    // kab_bandr_kernel: not nullptr = every CTA counts itself here when it starts (hybrid
+                            // band plans: the single-CTA kernel is launched behind kab_gate_kernel, which waits
+                            // until the clusters hold their SMs)
 };
+
+// Waits until *counter has reached target (a count that only grows): see KabParams::started.
+__global__ void kab_gate_kernel(const unsigned int *counter, unsigned int target) {
+  if (threadIdx.x == 0) {
+    unsigned int v;
+    for (;;) {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+      if ((int)(v - target) >= 0) break;
+      __nanosleep(500);
+    }
+  }
+}
 
 // max_move < 4 in the kernels written for four moves: x + 0.0f == x for every candidate (finite or
 // -inf, never -0), x + -inf == -inf.  MM == false (max_move 4): nothing is emitted.

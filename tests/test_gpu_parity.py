@@ -325,6 +325,30 @@ def test_wide_vocabulary_gather_mode_nonfinite_and_bad_label(kab):
     assert scores[a:].tobytes() == rs[a:].tobytes() and final[2].tobytes() == rf[2].tobytes()
 
 
+def test_hybrid_band_plan(kab, monkeypatch):
+    """A multi-book job: hundreds of chapter-like lattices and a few much longer ones.  The plan gives
+    the longest to kab_bandr_kernel clusters and the rest to the single-CTA kernel, side by side
+    (KAB_BAND_KERNEL_HYBRID); the same batch through the single kernel alone and through a forced
+    one-lattice split gives the same bits."""
+    from kokoro_align_b200 import synth
+    rng = np.random.default_rng(6100)
+    T = np.concatenate([[30000, 28000, 26000], rng.integers(1500, 3501, 700)])
+    L = np.maximum(1, np.round(0.14 * T)).astype(np.int64)
+    perm = rng.permutation(len(T))                       # the long ones anywhere in the batch
+    T, L = T[perm], L[perm]
+    lp, t_off, labels, l_off = synth.make_batch_fast(T, L, seed=6101)
+    lp = (np.round(lp * 8) / 8).astype(np.float32)       # ties
+    info = _compare_batch(kab, lp, t_off, labels, l_off)
+    assert info.band_kernel == 5 and info.band_cluster == 7 and info.n_class[1] == len(T)
+    monkeypatch.setenv("KAB_BAND_HYBRID", "0")
+    info = _compare_batch(kab, lp, t_off, labels, l_off)
+    assert info.band_kernel == 1
+    monkeypatch.setenv("KAB_BAND_HYBRID", "1")
+    n = 40                                               # a small plan, split by force; max_move 3
+    info = _compare_batch(kab, lp[:int(t_off[n])], t_off[:n + 1], labels[:int(l_off[n])], l_off[:n + 1], max_move=3)
+    assert info.band_kernel in (4, 5)
+
+
 def test_config4_banded_million_frames(kab):
     """BASELINE config 4(i): ONE lattice of T = 10^6 frames, L = 50 000 labels, the default
     1000-wide band (10^9 evaluated cells), bit-exact against the C oracle; then the same batch
