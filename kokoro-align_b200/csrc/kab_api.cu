@@ -536,6 +536,10 @@ int plan_create_impl(kab_plan **out, int device, int64_t B, const int64_t *t_off
     double sum_t = 0.0, max_t = 0.0;
     for (const KabLattice &d : pl->lists[Q_BAND]) { sum_t += d.T; max_t = std::max(max_t, (double)d.T); }
     const double est_r = std::max(max_t, sum_t / std::max(1, pl->sm_count / std::max(1, ncr))) * 70.0;
+    // (190 ns per frame is a lone lattice's latency in the single-CTA kernel; with every SM holding two of
+    // them a CTA slot's frames cost ~330 ns each -- 18 books on one GPU: 49 M frames / 296 slots, 54.5 ms.
+    // The estimates keep the one figure: with 330 in the throughput terms the split below was chosen
+    // less often and measured worse, 36.9 instead of 34.9 ms for 18 books on two GPUs.)
     const double est_b = std::max(max_t, sum_t / (double)(pl->sm_count * (pl->band_nw <= 16 ? 2 : 1))) * 190.0;
     const bool use_r = pl->band_ga || (r_ok && want_r != 0 && want_nc != 0 && want_q != 0 && (want_r >= 1 || want_nc >= 1 || est_r <= est_b));
     const bool use_q = !use_r && M == 4 && q_ok && want_q != 0 && want_nc != 0 && (want_q >= 1 || n_band <= pl->sm_count / ncq);
