@@ -185,6 +185,14 @@ struct kab_plan {
   // H2D copy of segment k+1, the kernels of segment k and the D2H copy of segment k-1 overlap
   std::vector<kab_plan *> segs;
   std::vector<int64_t> seg_b0;
+  // ... or, for a book (a few dozen chapter lattices, bound by the longest one): two sub-plans over the
+  // same arrays -- pipe[0] the longest chapters, whose rows are copied first and whose clusters start
+  // while the rest (pipe[1]) is still on its way
+  static constexpr int NPIPE = 3;  // the longest chapter | the next ones, up to a third of the frames | the rest
+  kab_plan *pipe[NPIPE] = {nullptr, nullptr, nullptr};
+  std::vector<std::pair<int64_t, int64_t>> pipe_rows[NPIPE];  // (first row, rows) of the copies, in order
+  cudaStream_t s_pipe[NPIPE] = {nullptr, nullptr, nullptr};   // ([0] unused: pipe[0] runs on `stream`)
+  cudaEvent_t ev_pipe_in[NPIPE] = {nullptr, nullptr, nullptr}, ev_pipe_done[NPIPE] = {nullptr, nullptr, nullptr};
   cudaStream_t s_in = nullptr, s_out = nullptr;
   std::vector<cudaEvent_t> ev_in, ev_cmp;
   bool is_child = false;
@@ -230,6 +238,15 @@ void host_teardown(kab_plan *pl) {
   for (kab_plan *c : pl->segs) plan_free(c);
   pl->segs.clear();
   pl->seg_b0.clear();
+  for (int k = 0; k < kab_plan::NPIPE; ++k) {
+    if (pl->pipe[k]) plan_free(pl->pipe[k]);
+    pl->pipe[k] = nullptr;
+    pl->pipe_rows[k].clear();
+    if (pl->ev_pipe_in[k]) cudaEventDestroy(pl->ev_pipe_in[k]);
+    if (pl->ev_pipe_done[k]) cudaEventDestroy(pl->ev_pipe_done[k]);
+    if (pl->s_pipe[k]) cudaStreamDestroy(pl->s_pipe[k]);
+    pl->ev_pipe_in[k] = nullptr; pl->ev_pipe_done[k] = nullptr; pl->s_pipe[k] = nullptr;
+  }
   for (cudaEvent_t e : pl->ev_in) cudaEventDestroy(e);
   for (cudaEvent_t e : pl->ev_cmp) cudaEventDestroy(e);
   pl->ev_in.clear();
@@ -1312,6 +1329,67 @@ int host_setup(kab_plan *pl) {
       }
     }
   }
+  // ---- a book: few lattices, the time of the longest.  Its rows go first and its clusters start at once.
+  {
+    const char *be = getenv("KAB_HOST_BOOK");
+    const std::vector<KabLattice> &bl = pl->lists[Q_BAND];  // (longest first)
+    if (pl->segs.empty() && !pl->sub && !pl->is_child && pl->band_r && !pl->band_ga && !pl->Vc && !pl->any_bad_label &&
+        pl->h_t_off[0] == 0 && bl.size() >= 4 && !(be && atoi(be) == 0) && (bytes_total >= (48ll << 20) || (be && atoi(be) >= 1))) {
+      double band_t = 0.0;
+      for (const KabLattice &d : bl) band_t += d.T;
+      constexpr int NP = kab_plan::NPIPE;
+      std::vector<uint8_t> m[NP];
+      for (int k = 0; k < NP; ++k) m[k].assign(B, k == NP - 1 ? 1 : 0);
+      // pipe 0: the longest chapter; pipe 1: the next ones while they stay within a third of the frames
+      size_t taken = 0, cnt[NP] = {0, 0, 0};
+      double acc = 0.0;
+      for (int k = 0; k + 1 < NP; ++k) {
+        while (taken + 1 < bl.size() && (k == 0 ? cnt[0] < 1 : (cnt[1] < 5 && acc + bl[taken].T <= 0.34 * band_t))) {
+          const KabLattice &d = bl[taken++];
+          acc += d.T;
+          m[k][(size_t)d.index] = 1; m[NP - 1][(size_t)d.index] = 0;
+          pl->pipe_rows[k].emplace_back(pl->h_t_off[(size_t)d.index], (int64_t)d.T);
+          ++cnt[k];
+        }
+      }
+      for (size_t b = 0; b < B;) {  // the other lattices: contiguous runs of rows
+        if (!m[NP - 1][b]) { ++b; continue; }
+        size_t e = b;
+        while (e < B && m[NP - 1][e]) ++e;
+        pl->pipe_rows[NP - 1].emplace_back(pl->h_t_off[b], pl->h_t_off[e] - pl->h_t_off[b]);
+        b = e;
+      }
+      const int32_t *lab = pl->h_labels.empty() ? nullptr : pl->h_labels.data();
+      int rcs[NP] = {KAB_OK, KAB_OK, KAB_OK};
+      auto make = [&](int k) {
+        if (k + 1 < NP && cnt[k] == 0) return;
+        rcs[k] = plan_create_impl(&pl->pipe[k], pl->device, (int64_t)B, pl->h_t_off.data(), lab, pl->h_l_off.data(), pl->V, pl->W, pl->M,
+                                  m[k].data(), k + 1 < NP ? 1 : -1);
+      };
+      {
+        std::vector<std::thread> th;
+        for (int k = 1; k < NP; ++k) th.emplace_back(make, k);
+        make(0);
+        for (auto &t : th) t.join();
+      }
+      for (int k = 0; k < NP; ++k)
+        if (rcs[k] != KAB_OK) return fail(rcs[k]);
+      // the clusters of the GPU: one per lattice of pipes 0 and 1, the others for the rest
+      int ncl_left = pl->band_nc > 0 ? pl->sm_count / pl->band_nc : 0;
+      for (int k = 0; k < NP; ++k) {
+        if (!pl->pipe[k]) continue;
+        pl->pipe[k]->is_child = true;
+        if (pl->pipe[k]->band_nc > 0 && !pl->pipe[k]->lists[Q_BAND].empty()) {
+          const int want_cl = k + 1 < NP ? (int)cnt[k] : std::max(1, ncl_left);
+          pl->pipe[k]->grid[Q_BAND] = std::min(pl->pipe[k]->grid[Q_BAND], want_cl * pl->pipe[k]->band_nc);
+          ncl_left -= want_cl;
+        }
+        if (k > 0) KAB_SETUP(cudaStreamCreateWithFlags(&pl->s_pipe[k], cudaStreamNonBlocking));
+        KAB_SETUP(cudaEventCreateWithFlags(&pl->ev_pipe_in[k], cudaEventDisableTiming));
+        KAB_SETUP(cudaEventCreateWithFlags(&pl->ev_pipe_done[k], cudaEventDisableTiming));
+      }
+    }
+  }
 #undef KAB_SETUP
   pl->host_ready = true;
   return KAB_OK;
@@ -1372,11 +1450,36 @@ int run_host_impl(kab_plan *pl, const HostRun &r) {
   };
   if (pl->segs.empty()) {  // small batch: one copy in, one run, one copy out
     cudaStream_t s = pl->stream;
-    KAB_CUDA(cudaMemcpyAsync(pl->d_lp, r.h_in, n * V * 4, cudaMemcpyHostToDevice, s));
     int rc = KAB_OK;
-    if (r.logits && (rc = kab_log_softmax_device(pl->d_lp, pl->d_lp, (int64_t)n, pl->V, s)) != KAB_OK) return rc;
-    rc = kab_plan_run_device(pl, pl->d_lp, pl->d_path, pl->d_lab, pl->d_sc, pl->d_fs, pl->d_st, s);
-    if (rc != KAB_OK) return rc;
+    if (pl->pipe[0]) {
+      // a book: the longest chapters' rows first, their clusters start while the others' rows arrive
+      constexpr int NP = kab_plan::NPIPE;
+      for (int k = 0; k < NP; ++k) {
+        if (!pl->pipe[k]) continue;
+        for (const auto &rr : pl->pipe_rows[k])
+          KAB_CUDA(cudaMemcpyAsync(pl->d_lp + rr.first * V, r.h_in + rr.first * V, (size_t)rr.second * V * 4, cudaMemcpyHostToDevice, pl->s_in));
+        KAB_CUDA(cudaEventRecord(pl->ev_pipe_in[k], pl->s_in));
+      }
+      for (int k = 0; k < NP; ++k) {
+        if (!pl->pipe[k]) continue;
+        cudaStream_t ck = k == 0 ? s : pl->s_pipe[k];
+        KAB_CUDA(cudaStreamWaitEvent(ck, pl->ev_pipe_in[k], 0));
+        if (r.logits)
+          for (const auto &rr : pl->pipe_rows[k])
+            if ((rc = kab_log_softmax_device(pl->d_lp + rr.first * V, pl->d_lp + rr.first * V, rr.second, pl->V, ck)) != KAB_OK) return rc;
+        rc = kab_plan_run_device(pl->pipe[k], pl->d_lp, pl->d_path, pl->d_lab, pl->d_sc, pl->d_fs, pl->d_st, ck);
+        if (rc != KAB_OK) return rc;
+        if (k > 0) {
+          KAB_CUDA(cudaEventRecord(pl->ev_pipe_done[k], ck));
+          KAB_CUDA(cudaStreamWaitEvent(s, pl->ev_pipe_done[k], 0));
+        }
+      }
+    } else {
+      KAB_CUDA(cudaMemcpyAsync(pl->d_lp, r.h_in, n * V * 4, cudaMemcpyHostToDevice, s));
+      if (r.logits && (rc = kab_log_softmax_device(pl->d_lp, pl->d_lp, (int64_t)n, pl->V, s)) != KAB_OK) return rc;
+      rc = kab_plan_run_device(pl, pl->d_lp, pl->d_path, pl->d_lab, pl->d_sc, pl->d_fs, pl->d_st, s);
+      if (rc != KAB_OK) return rc;
+    }
     if (r.h_lp_out) KAB_CUDA(cudaMemcpyAsync(r.h_lp_out, pl->d_lp, n * V * 4, cudaMemcpyDeviceToHost, s));
     if (arrays) {
       KAB_CUDA(cudaMemcpyAsync(r.h_path, pl->d_path, n * 4, cudaMemcpyDeviceToHost, s));

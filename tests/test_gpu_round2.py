@@ -271,6 +271,44 @@ def test_segment_records_match_numpy(kab):
             plan.run_host_segments(lp, [np.array([10, 5])] + indices[1:])
 
 
+def test_book_pipeline_run_host(kab, monkeypatch):
+    """kab_plan_run_host on a book: the longest chapters' rows are copied first and run in their own
+    sub-plan while the other chapters' rows arrive (forced here on a small book; a 400 MB book takes it
+    by itself).  Same bits as the oracle, from log-probs, and the same records / arrays through the
+    segment entry point; a chapter whose band dies keeps its status."""
+    from kokoro_align_b200 import synth
+    from oracle import ctc_oracle
+    T = np.array([2500, 9000, 700, 5000, 350, 3000, 4000, 6000, 1200])
+    L = np.maximum(1, np.round(0.14 * T)).astype(np.int64)
+    L[5] = 2900                                                  # S > 3T / 2: the 200-wide band loses the end state
+    lp, t_off, labels, l_off = synth.make_batch(T, L, seed=9700)
+    lp = (np.round(lp * 4) / 4).astype(np.float32)
+    rp, rl, rs, rf, rst = ctc_oracle.ctc_best_path_batch(lp, t_off, labels, l_off, 200, 4, n_threads=4)
+    monkeypatch.setenv("KAB_HOST_BOOK", "1")
+    with kab.AlignPlan(t_off, labels, l_off, 39, 200) as plan:
+        for _ in range(2):                                       # (the second run reuses the pipeline)
+            path, labs, scores, final, status = plan.run_host(lp)
+            np.testing.assert_array_equal(status, rst)
+            for b in np.flatnonzero(rst == 0):
+                a, e = int(t_off[b]), int(t_off[b + 1])
+                np.testing.assert_array_equal(path[a:e], rp[a:e])
+                np.testing.assert_array_equal(labs[a:e], rl[a:e])
+                assert scores[a:e].tobytes() == rs[a:e].tobytes() and final[b].tobytes() == rf[b].tobytes()
+        indices = [np.array([t // 3, 2 * t // 3, t]) for t in T]
+        rec, f2, st2, ex = plan.run_host_segments(lp, indices, arrays=True)
+        np.testing.assert_array_equal(st2, rst)
+        ok = np.repeat(rst == 0, 3)
+        want = _host_records(np.where(np.repeat(rst, T) == 0, rp, 0), rl, rs, t_off, indices)
+        assert rec[ok].tobytes() == want[ok].tobytes()
+    monkeypatch.setenv("KAB_HOST_BOOK", "0")
+    with kab.AlignPlan(t_off, labels, l_off, 39, 200) as plan:
+        p2, l2, s2, f2, st2 = plan.run_host(lp)
+    np.testing.assert_array_equal(st2, status)
+    good = np.repeat(status == 0, T)
+    np.testing.assert_array_equal(p2[good], path[good])
+    assert s2[good].tobytes() == scores[good].tobytes()
+
+
 def test_segment_records_long_segment_and_failed_lattice(kab):
     """A single 120 000-frame segment (more leaves than a warp keeps: the one-lane path) and a
     batch with a dead-band lattice (its records carry the status)."""
