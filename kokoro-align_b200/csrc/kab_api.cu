@@ -427,28 +427,81 @@ int plan_create_impl(kab_plan **out, int device, int64_t B, const int64_t *t_off
   // ---- classify, build the padded column table (numpy-style wrap of negative labels)
   std::vector<uint16_t> col16;
   std::vector<int32_t> status_init((size_t)B, 0);
-  col16.reserve((size_t)(pl->total_L + 16 * B + 16));
   int64_t bp_bytes = 0, scr_floats = 0, max_band_weff = 0;
   std::vector<uint8_t> hyb_mask;  // hybrid band plan: the lattices of the sub-plan
   int hyb_k = 0;                  // ... and its clusters
   kab_plan_info &info = pl->info;
   info.n_lattices = B; info.device = device; info.total_frames = pl->total_T;
-  std::vector<int64_t> distinct_words(1024, 0);
   const int n_mask = (V + 63) / 64;
+  // The label scans (range check, distinct labels, column table) are independent per lattice and are
+  // most of this function for a batch of 10 000 segments (4.5 of 5 ms): several host threads do them
+  // ahead of the (cheap, sequential) classification below.
+  struct LatFacts { uint8_t bad, special, compact; int32_t distinct; int64_t col_off; };
+  std::vector<LatFacts> facts((size_t)B);
+  auto for_lattices = [&](auto &&fn) {  // fn(b, scratch words) over the plan's lattices
+    const unsigned hw = std::thread::hardware_concurrency();
+    const int nt = (B >= 2048 && pl->total_L >= 65536 && hw >= 4 && !getenv("KAB_SERIAL_SETUP")) ? (int)std::min<unsigned>(8, hw / 2) : 1;
+    auto work = [&](int t) {
+      std::vector<int64_t> words((size_t)std::max(n_mask, 1), 0);
+      const int64_t b0 = B * t / nt, b1 = B * (t + 1) / nt;
+      for (int64_t b = b0; b < b1; ++b)
+        if (!mask || mask[b]) fn(b, words.data());
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto &x : th) x.join();
+  };
+  for_lattices([&](int64_t b, int64_t *distinct_mask) {  // pass A: facts (and the compact numbering's gather row)
+    const int64_t T = t_off[b + 1] - t_off[b], L = l_off[b + 1] - l_off[b], S = 2 * L + 1;
+    const int32_t *lab = labels + l_off[b];
+    LatFacts f{};
+    std::fill(distinct_mask, distinct_mask + n_mask, (int64_t)0);
+    for (int64_t l = 0; l < L; ++l) {
+      if (lab[l] < -V || lab[l] >= V) { f.bad = 1; break; }
+      if (lab[l] <= 0) f.special = 1;
+      const int32_t c = lab[l] < 0 ? lab[l] + V : lab[l];
+      if (!(distinct_mask[c >> 6] >> (c & 63) & 1)) { distinct_mask[c >> 6] |= (int64_t)1 << (c & 63); ++f.distinct; }
+    }
+    const bool ga = pl->band_ga && !f.special && band_shaped(T, S);
+    if (!f.bad && pl->Vc && !f.special && !ga && f.distinct + 1 <= pl->Vc) {
+      // compact numbering: blank 0, then the lattice's distinct label columns in ascending order
+      f.compact = 1;
+      int32_t *g = h_gather.data() + (size_t)b * pl->Vc;
+      int32_t n = 1;
+      for (int w = 0; w < n_mask; ++w)
+        for (int64_t m = distinct_mask[w]; m; m &= m - 1) g[n++] = w * 64 + __builtin_ctzll((unsigned long long)m);
+    }
+    facts[(size_t)b] = f;
+  });
+  {  // offsets of the padded column table (a bad-label lattice has no columns)
+    int64_t off = 0;
+    for (int64_t b = 0; b < B; ++b) {
+      if (mask && !mask[b]) continue;
+      facts[(size_t)b].col_off = off;
+      if (!facts[(size_t)b].bad) off += align_up(l_off[b + 1] - l_off[b], 8) + 8;
+    }
+    col16.assign((size_t)off, 0);
+  }
+  for_lattices([&](int64_t b, int64_t *) {  // pass B: the column table
+    const LatFacts &f = facts[(size_t)b];
+    if (f.bad) return;
+    const int64_t L = l_off[b + 1] - l_off[b];
+    const int32_t *lab = labels + l_off[b];
+    uint16_t *c = col16.data() + f.col_off;
+    if (f.compact) {
+      const int32_t *g = h_gather.data() + (size_t)b * pl->Vc;
+      const int32_t n = f.distinct + 1;
+      for (int64_t l = 0; l < L; ++l) c[l] = (uint16_t)(std::lower_bound(g + 1, g + n, lab[l]) - g);
+    } else {
+      for (int64_t l = 0; l < L; ++l) c[l] = (uint16_t)(lab[l] < 0 ? lab[l] + V : lab[l]);
+    }
+  });
   for (int64_t b = 0; b < B; ++b) {
     if (mask && !mask[b]) continue;
     const int64_t T = t_off[b + 1] - t_off[b], L = l_off[b + 1] - l_off[b], S = 2 * L + 1;
-    const int32_t *lab = labels + l_off[b];
-    bool bad = false, special = false;
-    int64_t *distinct_mask = distinct_words.data();  // (V <= 65535: 1024 words; only the first n_mask are in use)
-    std::fill(distinct_mask, distinct_mask + n_mask, (int64_t)0);
-    int64_t distinct = 0;
-    for (int64_t l = 0; l < L; ++l) {
-      if (lab[l] < -V || lab[l] >= V) { bad = true; break; }
-      if (lab[l] <= 0) special = true;
-      const int32_t c = lab[l] < 0 ? lab[l] + V : lab[l];
-      if (!(distinct_mask[c >> 6] >> (c & 63) & 1)) { distinct_mask[c >> 6] |= (int64_t)1 << (c & 63); ++distinct; }
-    }
+    const bool bad = facts[(size_t)b].bad != 0, special = facts[(size_t)b].special != 0;
+    const int64_t distinct = facts[(size_t)b].distinct;
     if (bad) {  // reference: IndexError at align.py:77
       status_init[(size_t)b] = KAB_ST_BAD_LABEL;
       pl->any_bad_label = true;
@@ -458,21 +511,8 @@ int plan_create_impl(kab_plan **out, int device, int64_t B, const int64_t *t_off
     d.t_off = t_off[b];
     d.lab_off = l_off[b];
     d.T = (int32_t)T; d.L = (int32_t)L; d.index = (int32_t)b;
-    d.col_off = (int64_t)col16.size();
+    d.col_off = facts[(size_t)b].col_off;
     const bool ga = pl->band_ga && !special && band_shaped(T, S);  // gather mode: the labels stay column numbers
-    if (pl->Vc && !special && !ga && distinct + 1 <= pl->Vc) {
-      // compact numbering: blank 0, then the lattice's distinct label columns in ascending order
-      int32_t *g = h_gather.data() + (size_t)b * pl->Vc;
-      int32_t n = 1;
-      for (int w = 0; w < n_mask; ++w)
-        for (int64_t m = distinct_mask[w]; m; m &= m - 1) g[n++] = w * 64 + __builtin_ctzll((unsigned long long)m);
-      for (int64_t l = 0; l < L; ++l)
-        col16.push_back((uint16_t)(std::lower_bound(g + 1, g + n, lab[l]) - g));
-    } else {
-      for (int64_t l = 0; l < L; ++l) col16.push_back((uint16_t)(lab[l] < 0 ? lab[l] + V : lab[l]));
-    }
-    while (col16.size() % 8) col16.push_back(0);
-    for (int k = 0; k < 8; ++k) col16.push_back(0);
 
     // max_move 1 .. 3 run in the same kernels (their MM instantiations turn the excluded moves'
     // candidates into -inf); more than four moves only exist in the generic kernel
