@@ -26,6 +26,7 @@
 #include "kab_wide.cuh"
 #include "kab_common.cuh"
 #include "kab_compact.cuh"
+#include "kab_debug.h"
 #include "kab_generic.cuh"
 #include "kab_softmax.cuh"
 #include "kab_segstats.cuh"
@@ -928,37 +929,11 @@ int kab_plan_run_device(kab_plan *pl, const float *d_log_probs, int32_t *d_best_
   if (!pl->lists[Q_BAND].empty()) {
     KabParams pb = pl->band_ga ? p : pf; pb.queue = pl->d_queue + Q_BAND;
     if (pl->band_ga) { pb.stage_frames = KAB_BR_F; pb.stage_bytes = 64; }  // (no emission stages: the geometry's minimum)
-#ifdef KAB_BAND_TIMING
-    static long long *dbg = nullptr;
-    if (!dbg) cudaMalloc((void **)&dbg, 32 * 8 * sizeof(long long));
-    cudaMemsetAsync(dbg, 0, 32 * 8 * sizeof(long long), stream);
-    pb.debug = dbg;
-#endif
+    KabBandTiming band_timing(pb, stream, pl->band_nw);  // (development builds only: kab_debug.h)
     if (pl->band_nc > 0) {
       if (!pl->band_r) KAB_CUDA(cudaMemsetAsync(pl->d_band_fifo, 0, (size_t)pl->band_fifo_bytes, stream));  // (bandr: mailboxes in shared memory)
       pb.fifo = pl->d_band_fifo;
-#ifdef KAB_BANDP_TIMING
-      static long long *pdbg = nullptr;
-      if (!pdbg) cudaMalloc((void **)&pdbg, (32 * 16 + 8) * sizeof(long long));
-      cudaMemsetAsync(pdbg, 0, (32 * 16 + 8) * sizeof(long long), stream);
-      pb.debug = pdbg;
-      struct BandpDbgPrint {
-        long long *d; cudaStream_t s; int nw;
-        ~BandpDbgPrint() {
-          long long h[32 * 16 + 8];
-          cudaStreamSynchronize(s);
-          cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
-          for (int w = 0; w < nw; ++w) {
-            const long long *x = h + w * 16;
-            const double n = (double)(x[7] ? x[7] : 1);
-            fprintf(stderr, "warp %2d: per group: ghost %5.0f (guard %4.0f) emis %4.0f comp %5.0f pub %4.0f rel %4.0f bp %4.0f | total %lld cyc, %lld groups, need %lld, safe %lld, wait/need %.0f, first-try %lld, comp safe %.0f slow %.0f\n",
-                    w, x[0] / n, x[8] / n, x[1] / n, x[2] / n, x[3] / n, x[4] / n, x[5] / n, x[6], x[7], x[9], x[10], x[9] ? (double)x[11] / x[9] : 0.0, x[12],
-                    x[10] ? (double)(x[2] - x[13]) / x[10] : 0.0, x[7] - x[10] ? (double)x[13] / (x[7] - x[10]) : 0.0);
-          }
-          fprintf(stderr, "backtrack %lld cyc\n", h[32 * 16]);
-        }
-      } pdbg_print{pdbg, stream, KAB_BP_CW * pl->band_nc};
-#endif
+      KabBandpTiming bandp_timing(pb, stream, KAB_BP_CW * pl->band_nc);
       cudaLaunchConfig_t cfg{};
       cudaLaunchAttribute at[1];
       at[0].id = cudaLaunchAttributeClusterDimension;
@@ -972,94 +947,9 @@ int kab_plan_run_device(kab_plan *pl, const float *d_log_probs, int32_t *d_best_
       const int n_band = (int)pl->lists[Q_BAND].size();
       const dim3 mg((unsigned)pl->bt_blocks, (unsigned)((pl->bt_max_wl + KAB_BT_THREADS - 1) / KAB_BT_THREADS));
       if (pl->band_q) {
-#ifdef KAB_BANDQ_TIMING
-        static long long *qdbg = nullptr;
-        if (!qdbg) cudaMalloc((void **)&qdbg, (64 * 28 + 8) * sizeof(long long));
-        cudaMemsetAsync(qdbg, 0, (64 * 28 + 8) * sizeof(long long), stream);
-        pb.debug = qdbg;
-        struct BandqDbgPrint {
-          long long *d; cudaStream_t s; int nw;
-          ~BandqDbgPrint() {
-            static long long h[64 * 28 + 8];
-            cudaStreamSynchronize(s);
-            cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
-            long long ct[4] = {0, 0, 0, 0}, cn[4] = {0, 0, 0, 0}, cw[4] = {0, 0, 0, 0};
-            for (int w = 0; w < nw; ++w)
-              for (int k = 0; k < 4; ++k) {
-                const long long *c = h + 64 * 16 + 8 + w * 12;
-                ct[k] += c[k]; cn[k] += c[4 + k]; cw[k] += c[8 + k];
-              }
-            const char *names[4] = {"free / head (no message, edge body)", "no message, safe body", "message + edge body", "message + safe body"};
-            for (int k = 0; k < 4; ++k)
-              fprintf(stderr, "groups [%s]: %lld, %.0f cycles each, of which waiting %.0f\n", names[k], cn[k],
-                      cn[k] ? (double)ct[k] / cn[k] : 0.0, cn[k] ? (double)cw[k] / cn[k] : 0.0);
-            for (int w = 0; w < nw; w += 9) {
-              const long long *x = h + w * 16;
-              const double n = (double)(x[7] ? x[7] : 1);
-              fprintf(stderr, "warp %2d: per group: ghost %5.0f emis %4.0f comp %5.0f pub %4.0f bp %4.0f rel %4.0f | total %lld cyc = %.0f / group, %lld groups, need %lld, safe %lld, wait/need %.0f, comp safe %.0f slow %.0f\n",
-                      w, x[0] / n, x[1] / n, x[2] / n, x[3] / n, x[5] / n, x[4] / n, x[6], x[6] / n, x[7], x[9], x[10], x[9] ? (double)x[11] / x[9] : 0.0,
-                      x[10] ? (double)(x[2] - x[13]) / x[10] : 0.0, x[7] - x[10] ? (double)x[13] / (x[7] - x[10]) : 0.0);
-            }
-          }
-        } qdbg_print{qdbg, stream, pl->band_cw * pl->band_nc};
-#endif
+        KabBandqTiming bandq_timing(pb, stream, pl->band_cw * pl->band_nc);
         const int nwt = pl->band_cw * pl->band_nc;
-#ifdef KAB_BR_TRACE2
-        static long long *tdbg = nullptr;
-        if (!tdbg) cudaMalloc((void **)&tdbg, 64 * 256 * 4 * sizeof(long long));
-        cudaMemsetAsync(tdbg, 0, 64 * 256 * 4 * sizeof(long long), stream);
-        pb.debug = tdbg;
-        struct Trace2Dump {
-          long long *d; cudaStream_t s;
-          ~Trace2Dump() {
-            if (const char *tf = getenv("KAB_TRACE_FILE")) {
-              std::vector<long long> tr((size_t)64 * 256 * 4);
-              cudaStreamSynchronize(s);
-              cudaMemcpy(tr.data(), d, tr.size() * sizeof(long long), cudaMemcpyDeviceToHost);
-              if (FILE *f = fopen(tf, "wb")) { fwrite(tr.data(), sizeof(long long), tr.size(), f); fclose(f); }
-            }
-          }
-        } trace2_dump{tdbg, stream};
-#endif
-#ifdef KAB_BANDR_TIMING
-        static long long *rdbg = nullptr;
-        const size_t rdbg_n = 64 * 26 + (size_t)64 * 16384 * 2;
-        if (!rdbg) cudaMalloc((void **)&rdbg, rdbg_n * sizeof(long long));
-        cudaMemsetAsync(rdbg, 0, rdbg_n * sizeof(long long), stream);
-        pb.debug = rdbg;
-        struct BandrDbgPrint {
-          long long *d; cudaStream_t s; int nw;
-          ~BandrDbgPrint() {
-            static long long h[64 * 26];
-            cudaStreamSynchronize(s);
-            cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
-            if (const char *tf = getenv("KAB_TRACE_FILE")) {  // per-group start times of every compute warp
-              std::vector<long long> tr((size_t)64 * 16384 * 2);
-              cudaMemcpy(tr.data(), d + 64 * 26, tr.size() * sizeof(long long), cudaMemcpyDeviceToHost);
-              if (FILE *f = fopen(tf, "wb")) { fwrite(tr.data(), sizeof(long long), tr.size(), f); fclose(f); }
-            }
-            long long a[16] = {0};
-            for (int w = 0; w < nw; ++w)
-              for (int k = 0; k < 15; ++k) a[k] += h[w * 16 + k];
-            const double n = (double)(a[6] ? a[6] : 1);
-            fprintf(stderr, "compute warps, per group: tile %.0f msg %.0f (waiting %.0f) frames %.0f pub %.0f bp %.0f | total %.0f cycles / group\n",
-                    a[0] / n, a[1] / n, a[8] / n, a[2] / n, a[3] / n, a[4] / n, a[5] / n);
-            fprintf(stderr, "  groups without a message: %lld, %.0f cycles each (waiting %.0f); with: %lld, %.0f cycles each (waiting %.0f)\n",
-                    a[10], a[10] ? (double)a[9] / a[10] : 0.0, a[10] ? (double)a[11] / a[10] : 0.0,
-                    a[13], a[13] ? (double)a[12] / a[13] : 0.0, a[13] ? (double)a[14] / a[13] : 0.0);
-            long long ft = 0, fn = 0;
-            for (int w = 0; w < nw; ++w) { ft += h[64 * 24 + w * 2]; fn += h[64 * 24 + w * 2 + 1]; }
-            fprintf(stderr, "  fast-path groups: %lld of %lld, %.0f cycles each; the others %.0f cycles each\n", fn, a[6], fn ? (double)ft / fn : 0.0,
-                    a[6] - fn ? (double)(a[5] - ft) / (a[6] - fn) : 0.0);
-            long long b[8] = {0};
-            for (int w = 0; w < nw; ++w)
-              for (int k = 0; k < 6; ++k) b[k] += h[64 * 16 + w * 8 + k];
-            const double m = (double)(b[5] ? b[5] : 1);
-            fprintf(stderr, "prep warps, per group: waiting for the slot %.0f, tile %.0f, stage / backpointers %.0f | total %.0f, safe groups %.0f %%\n",
-                    b[0] / m, b[1] / m, b[2] / m, b[3] / m, 100.0 * b[4] / m);
-          }
-        } rdbg_print{rdbg, stream, nwt};
-#endif
+        KabBandrTiming bandr_timing(pb, stream, nwt);
         if (pl->band_r) {
           if (pl->band_ga) {
             if (pl->M == 4)
@@ -1103,40 +993,10 @@ int kab_plan_run_device(kab_plan *pl, const float *d_log_probs, int32_t *d_best_
         else kab_band_kernel<1024, true><<<bg, bb, pl->smem[Q_BAND], stream>>>(pl->d_lists[Q_BAND], nbl, pb);
       }
     }
-#ifdef KAB_BAND_TIMING
-    {
-      long long h[32 * 8];
-      cudaStreamSynchronize(stream);
-      cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
-      for (int w = 0; w < pl->band_nw; ++w)
-        fprintf(stderr, "warp %2d: fast %lld cyc / %lld groups, slow %lld / %lld, epi %lld, bar %lld, post %lld, total %lld\n", w,
-                h[w * 8 + 0], h[w * 8 + 1], h[w * 8 + 2], h[w * 8 + 3], h[w * 8 + 4], h[w * 8 + 5], h[w * 8 + 6], h[w * 8 + 7]);
-    }
-#endif
   }
   if (!pl->lists[Q_WIDE].empty()) {
     KAB_CUDA(cudaMemsetAsync(pl->d_wide_ws, 0, (size_t)pl->wide_ws_bytes, stream));
-#ifdef KAB_WIDE_TIMING
-    static long long *wdbg2 = nullptr;
-    if (!wdbg2) cudaMalloc((void **)&wdbg2, 64 * sizeof(long long));
-    cudaMemsetAsync(wdbg2, 0, 64 * sizeof(long long), stream);
-    pf.debug = wdbg2;
-    struct WideDbgPrint {
-      long long *d; cudaStream_t s;
-      ~WideDbgPrint() {
-        long long h[64];
-        cudaStreamSynchronize(s);
-        cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
-        const char *nm[6] = {"w0", "w1", "w2", "w3", "mid", "last"};
-        for (int w = 0; w < 6; ++w) {
-          const long long *x = h + w * 8;
-          const double n = (double)(x[7] ? x[7] : 1);
-          fprintf(stderr, "%4s: per group: ghost %6.0f emis %5.0f comp %6.0f pub %6.0f rest %5.0f | prefetch misses %lld of %lld groups, total %lld cyc\n",
-                  nm[w], x[0] / n, x[1] / n, x[2] / n, x[3] / n, x[4] / n, x[5], x[7], x[6]);
-        }
-      }
-    } wdbg_print{wdbg2, stream};
-#endif
+    KabWideTiming wide_timing(pf, stream);
     // cooperative launch: the warps of the chain spin on each other, so the whole grid has to be
     // resident -- the runtime checks that instead of letting the kernel hang
     const KabLattice *wl = pl->d_lists[Q_WIDE];
