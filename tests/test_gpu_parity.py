@@ -340,6 +340,27 @@ def test_hybrid_band_plan(kab, monkeypatch):
     lp = (np.round(lp * 8) / 8).astype(np.float32)       # ties
     info = _compare_batch(kab, lp, t_off, labels, l_off)
     assert info.band_kernel == 5 and info.band_cluster == 7 and info.n_class[1] == len(T)
+    # the same hybrid plan launched back to back on two streams, nothing synchronised in between (the
+    # gate's counter only grows), and captured into a CUDA graph that is replayed: same results every time
+    import torch
+    from oracle import ctc_oracle
+    rp = ctc_oracle.ctc_best_path_batch(lp, t_off, labels, l_off, 1000, 4, n_threads=8)[0]
+    d_lp = torch.from_numpy(lp).cuda()
+    with kab.AlignPlan(t_off, labels, l_off, 39) as plan:
+        s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+        outs = [plan.run_torch(d_lp, stream=(s1 if k % 2 else s2)) for k in range(4)]
+        torch.cuda.synchronize()
+        for o in outs:
+            assert (o[4].cpu().numpy() == 0).all()
+            np.testing.assert_array_equal(o[0].cpu().numpy(), rp)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s1):
+            o = plan.run_torch(d_lp, stream=s1)
+        for _ in range(3):
+            o[0].zero_()
+            g.replay()
+            torch.cuda.synchronize()
+            np.testing.assert_array_equal(o[0].cpu().numpy(), rp)
     monkeypatch.setenv("KAB_BAND_HYBRID", "0")
     info = _compare_batch(kab, lp, t_off, labels, l_off)
     assert info.band_kernel == 1
