@@ -591,9 +591,16 @@ int plan_create_impl(kab_plan **out, int device, int64_t B, const int64_t *t_off
     // band): kab_bandr.cuh ~70 ns per frame on one of sm_count / ncr clusters that pull lattices from
     // the work queue, kab_band.cuh ~190 ns per frame with two lattices per SM.  A book (36 chapters)
     // is bound by its longest chapter -> bandr; hundreds of chapters at once -> the single-CTA kernel.
-    double sum_t = 0.0, max_t = 0.0;
-    for (const KabLattice &d : pl->lists[Q_BAND]) { sum_t += d.T; max_t = std::max(max_t, (double)d.T); }
-    const double est_r = std::max(max_t, sum_t / std::max(1, pl->sm_count / std::max(1, ncr))) * 70.0;
+    double sum_t = 0.0, max_t = 0.0, bt_steps = 0.0;
+    for (const KabLattice &d : pl->lists[Q_BAND]) {
+      sum_t += d.T; max_t = std::max(max_t, (double)d.T);
+      bt_steps += (double)d.T * (double)std::min<int64_t>(W, 2 * (int64_t)d.L + 1);
+    }
+    // (bandr: 70 ns per frame for the longest lattice; with every cluster of the GPU busy on a queue of
+    // lattices ~90 ns per frame of a cluster's share, plus the map walkers of the parallel traceback at
+    // 1.85e12 steps/s -- 162 chapters on one GPU: 60.6 ms measured, 59 estimated; the first version of
+    // this estimate (70 ns, no traceback) said 41 and took the plan away from the single-CTA kernel's 49)
+    const double est_r = std::max(max_t * 70.0, sum_t / std::max(1, pl->sm_count / std::max(1, ncr)) * 90.0) + bt_steps * 0.55e-3;
     // (190 ns per frame is a lone lattice's latency in the single-CTA kernel; with every SM holding two of
     // them a CTA slot's frames cost ~330 ns each -- 18 books on one GPU: 49 M frames / 296 slots, 54.5 ms.
     // The estimates keep the one figure: with 330 in the throughput terms the split below was chosen
