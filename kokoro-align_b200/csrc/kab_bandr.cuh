@@ -1,7 +1,7 @@
 // kab_bandr.cuh -- warp-specialised cluster band kernel: the recurrence warps do NOTHING but the
 // recurrence.  Same shapes, ring, lanes and backpointer words as kab_bandq.cuh (two states per
-// lane, 12 ghost lanes, 40 owned ring slots per warp, 8 compute warps per CTA, clusters of
-// NC <= 8 CTAs; KabBtLayoutQ for the traceback).
+// lane, 12 ghost lanes, 40 owned ring slots per warp; KAB_BR_CW = 4 compute warps per CTA, one per
+// scheduler, clusters of NC <= 8 CTAs; KabBtLayoutQ for the traceback).
 //
 // Why (measured with the KAB_BANDQ_TIMING build and tools/ubench/chain.cu on B200): the frame of
 // the two-states-per-lane update is a dependent chain SHFL.UP (24.9 cycles) -> FADD2 (4.7) ->
@@ -22,7 +22,18 @@
 // st.shared::cluster per (score, seq) word, no mbarrier, no L2 round trip), one STS of the
 // backpointer word.  The prep warp also owns the ring bookkeeping (aliases, recycling, label
 // columns), releases the emission stages, and issues the bulk stores of its compute warp's
-// backpointer blocks.  A producer warp stages emission rows by bulk copies and checks finiteness.
+// backpointer blocks.  A producer warp stages emission rows by bulk copies and writes the window
+// table of every chunk (finiteness is checked by kab_finite_rows_kernel behind this kernel).
+//
+// What the chain's period turned out to be: (1) a warp whose ring slots
+// are recycled above the window rejoins the chain every 18 groups -- any start-up lag it is given
+// there is paid on the whole lattice, so it joins at once, through the common path; (2) after
+// that the chain runs at its minimal lag and its period is ONE warp's own work per group, hence
+// the common path of the compute warp: two groups per pass in a compact loop of its own, inline
+// polls, predicated end-of-group stores, addresses precomputed, two shared register pairs for the
+// three packed adds of a frame.
+// GA (template parameter): gather mode for wide vocabularies -- the prep warps read the emissions
+// from global memory, the producer warp prefetches the rows into L2.
 #pragma once
 #include "kab_band.cuh"
 #include "kab_bandp.cuh"
