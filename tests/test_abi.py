@@ -30,6 +30,18 @@ def test_library_exports_every_declared_symbol():
     assert L.kab_error_string(-2) == b"bad argument"
 
 
+def test_band_kernel_codes_match_the_header():
+    """kab_plan_info.band_kernel: the Python mirror names exactly the KAB_BAND_KERNEL_* codes of the
+    header, and the struct mirrors have the header's sizes."""
+    from kokoro_align_b200 import _lib
+    text = open(os.path.join(ROOT, "include", "kokoro_align_b200.h")).read()
+    codes = {name: int(v) for name, v in re.findall(r"#define\s+KAB_BAND_KERNEL_(\w+)\s+(\d+)", text)}
+    assert codes == {"CTA": 1, "CLUSTER": 2, "CLUSTER2": 3, "SPEC": 4, "HYBRID": 5}
+    assert sorted(k for k in _lib.BAND_KERNELS if k) == sorted(codes.values())
+    assert "kab_bandr_kernel" in _lib.BAND_KERNELS[codes["SPEC"]] and "kab_band_kernel" in _lib.BAND_KERNELS[codes["HYBRID"]]
+    assert ctypes.sizeof(_lib.SegmentRecord) == 24
+
+
 def test_reference_signatures():
     from kokoro_align_b200 import align
     sig = inspect.signature(align.ctc_best_path)
